@@ -1,0 +1,208 @@
+// api.cu - extern "C" surface of libft8b200.so (see include/ft8b200.h) and the chunked pipeline.
+#include <cmath>
+#include <cstring>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace ft8b {
+
+std::atomic<int64_t> g_launches{0};
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+// implemented in stft.cu / sync.cu / decode.cu
+int stft_db(const void *, int, int64_t, int64_t, int64_t, int, int, int, int, int, int64_t, int64_t, double *, cudaStream_t);
+int release_plans();
+int sync_scores(const double *, int64_t, int, int, int, int, double *, cudaStream_t);
+int select_candidates(const double *, int64_t, int, int, int, int, double, int32_t *, int32_t *, double *, int32_t *,
+                      int32_t *, cudaStream_t);
+int decode_candidates(const double *, int64_t, int, int, int, int, const int32_t *, const int32_t *, const int32_t *, int,
+                      int, uint8_t *, int32_t *, int32_t *, int32_t *, uint8_t *, double *, uint8_t *, cudaStream_t);
+int ldpc_crc(const double *, int64_t, int, uint8_t *, int32_t *, int32_t *, int32_t *, uint8_t *, uint8_t *, cudaStream_t);
+int extract_llr(const double *, int64_t, int, int, int, int, const int32_t *, const int32_t *, const int32_t *, int, int,
+                double *, uint8_t *, int32_t *, cudaStream_t);
+int normalize_llr(double *, int64_t, cudaStream_t);
+int ldpc_check(const uint8_t *, int64_t, int32_t *, cudaStream_t);
+
+static int default_chunk_slots(int64_t per_slot_bytes) {
+    // keep the chunk's float64 spectrogram + score map around half of B200's ~126 MB L2
+    int64_t c = (64ll << 20) / (per_slot_bytes > 0 ? per_slot_bytes : 1);
+    if (c < 1) c = 1;
+    if (c > 4096) c = 4096;
+    return (int)c;
+}
+
+struct Geometry {
+    int nperseg, hop, nfft, F, t0, nt, nf;
+    int64_t T_all, T;
+    int64_t mag_elems, score_elems;   // per slot
+};
+
+static int geometry(const ft8b_decode_params *p, int64_t n_samples, Geometry *g) {
+    ft8b_plan(p->sample_rate, p->bins_per_tone, p->steps_per_symbol, &g->nperseg, &g->hop, &g->nfft);
+    if (g->nperseg < 1 || g->hop < 1 || g->nfft < g->nperseg) FT8B_ARG_FAIL("decode: bad sample_rate/oversampling");
+    g->T_all = ft8b_num_frames(n_samples, g->nperseg, g->hop);
+    if (p->bin_lo < 0 || p->bin_hi < p->bin_lo || p->bin_hi > (g->nfft + 1) / 2) FT8B_ARG_FAIL("decode: bad bin range");
+    if (p->frame_lo < 0 || p->frame_hi < p->frame_lo || p->frame_hi > g->T_all) FT8B_ARG_FAIL("decode: bad frame range");
+    g->F = p->bin_hi - p->bin_lo;
+    g->T = p->frame_hi - p->frame_lo;
+    if (g->T > 0x7fffffff) FT8B_ARG_FAIL("decode: too many frames");
+    ft8b_search_ranges((int)g->T, g->F, p->steps_per_symbol, p->bins_per_tone, &g->t0, &g->nt, &g->nf);
+    g->mag_elems = g->T * (int64_t)g->F;
+    g->score_elems = (g->nt > 0 && g->nf > 0) ? (int64_t)g->nt * g->nf : 0;
+    return 0;
+}
+
+}  // namespace ft8b
+
+using namespace ft8b;
+
+extern "C" {
+
+int ft8b_version(void) { return FT8B_VERSION; }
+const char *ft8b_last_error(void) { return g_err; }
+int ft8b_release(void) { return release_plans(); }
+int64_t ft8b_launch_count(void) { return g_launches.load(); }
+
+int ft8b_plan(double fs, int bins_per_tone, int steps_per_symbol, int *nperseg, int *hop, int *nfft) {
+    if (!nperseg || !hop || !nfft || bins_per_tone < 1 || steps_per_symbol < 1 || !(fs > 0)) FT8B_ARG_FAIL("ft8b_plan: bad argument");
+    const int sps = (int)(0.16 * fs);                      // spectrogram_analyse.py:32
+    int overlap = sps - sps / steps_per_symbol;            // :33
+    const int n = (int)(fs / 6.25 * bins_per_tone);        // :34
+    if (overlap >= sps) overlap = sps - 1;                 // :42-43
+    *nperseg = sps;
+    *hop = sps - overlap;
+    *nfft = n;
+    return 0;
+}
+
+int64_t ft8b_num_frames(int64_t n, int nperseg, int hop) {
+    if (nperseg < 1 || hop < 1 || n < nperseg) return 0;   // :37-39
+    return (n - nperseg) / hop + 1;
+}
+
+int ft8b_search_ranges(int T, int F, int s, int b, int *t0, int *nt, int *nf) {
+    if (!t0 || !nt || !nf || s < 1 || b < 1) FT8B_ARG_FAIL("ft8b_search_ranges: bad argument");
+    const int nb = T / s;                                  // ftx_types.py:31-34
+    *t0 = -10 * s;                                         // ft8_decode.py:108
+    *nt = nb * s - s * (kND + 1) - *t0;
+    *nf = F - 7 * b;                                       // :109
+    return 0;
+}
+
+int ft8b_stft_db(const void *wave, int wave_dtype, int64_t n_slots, int64_t n_samples, int64_t slot_stride, int nperseg,
+                 int hop, int nfft, int bin_lo, int bin_hi, int64_t frame_lo, int64_t frame_hi, double *mag, void *stream) {
+    return stft_db(wave, wave_dtype, n_slots, n_samples, slot_stride, nperseg, hop, nfft, bin_lo, bin_hi, frame_lo,
+                   frame_hi, mag, (cudaStream_t)stream);
+}
+
+int ft8b_sync_scores(const double *mag, int64_t n_slots, int T, int F, int s, int b, double *scores, void *stream) {
+    return sync_scores(mag, n_slots, T, F, s, b, scores, (cudaStream_t)stream);
+}
+
+int ft8b_select_candidates(const double *scores, int64_t n_slots, int nt, int nf, int t0, int K, double min_score,
+                           int32_t *cand_time, int32_t *cand_freq, double *cand_score, int32_t *n_cand, int32_t *n_pass,
+                           void *stream) {
+    return select_candidates(scores, n_slots, nt, nf, t0, K, min_score, cand_time, cand_freq, cand_score, n_cand, n_pass,
+                             (cudaStream_t)stream);
+}
+
+int ft8b_decode_candidates(const double *mag, int64_t n_slots, int T, int F, int s, int b, const int32_t *cand_time,
+                           const int32_t *cand_freq, const int32_t *n_cand, int K, int max_iterations, uint8_t *ok,
+                           int32_t *ldpc_errors, int32_t *crc_extracted, int32_t *crc_calculated, uint8_t *payload,
+                           double *llr_out, uint8_t *plain_out, void *stream) {
+    return decode_candidates(mag, n_slots, T, F, s, b, cand_time, cand_freq, n_cand, K, max_iterations, ok, ldpc_errors,
+                             crc_extracted, crc_calculated, payload, llr_out, plain_out, (cudaStream_t)stream);
+}
+
+int ft8b_ldpc_crc(const double *llr, int64_t n_words, int max_iterations, uint8_t *plain, int32_t *ldpc_errors,
+                  int32_t *crc_extracted, int32_t *crc_calculated, uint8_t *payload, uint8_t *ok, void *stream) {
+    return ldpc_crc(llr, n_words, max_iterations, plain, ldpc_errors, crc_extracted, crc_calculated, payload, ok,
+                    (cudaStream_t)stream);
+}
+
+int ft8b_extract_llr(const double *mag, int64_t n_slots, int T, int F, int s, int b, const int32_t *cand_time,
+                     const int32_t *cand_freq, const int32_t *n_cand, int K, int normalize, double *llr, uint8_t *scratch_u8,
+                     int32_t *scratch_i32, void *stream) {
+    return extract_llr(mag, n_slots, T, F, s, b, cand_time, cand_freq, n_cand, K, normalize, llr, scratch_u8, scratch_i32,
+                       (cudaStream_t)stream);
+}
+
+int ft8b_normalize_llr(double *llr, int64_t n_words, void *stream) { return normalize_llr(llr, n_words, (cudaStream_t)stream); }
+
+int ft8b_ldpc_check(const uint8_t *bits, int64_t n_words, int32_t *errors, void *stream) {
+    return ldpc_check(bits, n_words, errors, (cudaStream_t)stream);
+}
+
+int64_t ft8b_decode_workspace_bytes(const ft8b_decode_params *p, int64_t n_slots, int64_t n_samples) {
+    if (!p) return FT8B_ERR_ARG;
+    Geometry g;
+    if (geometry(p, n_samples, &g)) return FT8B_ERR_ARG;
+    const int64_t per_slot = 8 * (g.mag_elems + g.score_elems);
+    int chunk = p->chunk_slots > 0 ? p->chunk_slots : default_chunk_slots(per_slot);
+    if (chunk > n_slots) chunk = (int)(n_slots > 0 ? n_slots : 1);
+    return per_slot * chunk + 256;
+}
+
+int ft8b_decode_slots(const void *wave, int wave_dtype, int64_t n_slots, int64_t n_samples, int64_t slot_stride,
+                      const ft8b_decode_params *p, void *workspace, int64_t workspace_bytes, int32_t *cand_time,
+                      int32_t *cand_freq, double *cand_score, int32_t *n_cand, uint8_t *ok, int32_t *ldpc_errors,
+                      int32_t *crc_extracted, int32_t *crc_calculated, uint8_t *payload, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!p || !wave || !workspace || !cand_time || !cand_freq || !cand_score || !n_cand || !ok || !ldpc_errors || !payload)
+        FT8B_ARG_FAIL("ft8b_decode_slots: null pointer");
+    if (wave_dtype != FT8B_DTYPE_F32 && wave_dtype != FT8B_DTYPE_F64) FT8B_ARG_FAIL("ft8b_decode_slots: bad dtype");
+    if (p->max_candidates < 0 || p->max_candidates > FT8B_MAX_CANDIDATES) {
+        set_error("ft8b_decode_slots: max_candidates=%d outside [0,%d]", p->max_candidates, FT8B_MAX_CANDIDATES);
+        return FT8B_ERR_UNSUPPORTED;
+    }
+    Geometry g;
+    int rc = geometry(p, n_samples, &g);
+    if (rc) return rc;
+    if (n_slots <= 0) return 0;
+    const int K = p->max_candidates;
+    const size_t elt = wave_dtype == FT8B_DTYPE_F32 ? 4 : 8;
+    const int64_t per_slot = 8 * (g.mag_elems + g.score_elems);
+    if (g.T <= 0 || g.F <= 0 || g.score_elems == 0 || K == 0) {
+        // nothing to search: the reference returns an empty list
+        FT8B_CUDA_TRY(cudaMemsetAsync(n_cand, 0, sizeof(int32_t) * n_slots, stream));
+        if (K > 0) {
+            FT8B_CUDA_TRY(cudaMemsetAsync(ok, 0, (size_t)n_slots * K, stream));
+            FT8B_CUDA_TRY(cudaMemsetAsync(ldpc_errors, 0, sizeof(int32_t) * (size_t)n_slots * K, stream));
+        }
+        return 0;
+    }
+    int chunk = p->chunk_slots > 0 ? p->chunk_slots : default_chunk_slots(per_slot);
+    if (chunk > n_slots) chunk = (int)n_slots;
+    if (workspace_bytes < per_slot * chunk) FT8B_ARG_FAIL("ft8b_decode_slots: workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)(per_slot * chunk));
+    double *mag = reinterpret_cast<double *>(workspace);
+    double *scores = mag + g.mag_elems * chunk;
+    for (int64_t s0 = 0; s0 < n_slots; s0 += chunk) {
+        const int64_t nb = (n_slots - s0 < chunk) ? (n_slots - s0) : chunk;
+        const char *w = reinterpret_cast<const char *>(wave) + (size_t)s0 * slot_stride * elt;
+        rc = stft_db(w, wave_dtype, nb, n_samples, slot_stride, g.nperseg, g.hop, g.nfft, p->bin_lo, p->bin_hi, p->frame_lo,
+                     p->frame_hi, mag, stream);
+        if (rc) return rc;
+        rc = sync_scores(mag, nb, (int)g.T, g.F, p->steps_per_symbol, p->bins_per_tone, scores, stream);
+        if (rc) return rc;
+        rc = select_candidates(scores, nb, g.nt, g.nf, g.t0, K, p->min_score, cand_time + s0 * K, cand_freq + s0 * K,
+                               cand_score + s0 * K, n_cand + s0, nullptr, stream);
+        if (rc) return rc;
+        rc = decode_candidates(mag, nb, (int)g.T, g.F, p->steps_per_symbol, p->bins_per_tone, cand_time + s0 * K,
+                               cand_freq + s0 * K, n_cand + s0, K, p->max_iterations, ok + s0 * K, ldpc_errors + s0 * K,
+                               crc_extracted ? crc_extracted + s0 * K : nullptr,
+                               crc_calculated ? crc_calculated + s0 * K : nullptr, payload + s0 * K * 10, nullptr, nullptr,
+                               stream);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+}  // extern "C"

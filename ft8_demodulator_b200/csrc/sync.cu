@@ -1,0 +1,379 @@
+// sync.cu - S2: Costas sync score map and candidate selection (float64).
+//
+// S2a replaces ft8_sync_score over the double loop of ft8_find_candidates (reference
+// ft8_decode.py:47-100, 108-124).  S2b replaces the heap bookkeeping of ft8_decode.py:127-140 with
+// its closed form: H = first K threshold passers in scan order; the best of H
+// is replaced by the first occurrence of the maximum over the later passers when that is strictly
+// greater; H sorted by descending score.
+//
+// S2a design: with t = t0 + rho + s*u (rho = time-oversampling phase) every waterfall column a
+// candidate touches has the same phase, col = rho + s*g, so each phase is a 1-D problem in symbol
+// units g.  One thread owns one abs_freq f and walks g = 0..nb-1 once, holding the 8 tone bins
+// f+tau*b of columns g and g+1 in registers.  The 7 Costas cells of a block are spread over 7
+// consecutive g, so 7 rotating accumulators carry the partial block sums S7(h) (h = g-k); a finished
+// S7(h) is added into score[u] for the three blocks u = h+10, h-26, h-62 (m = 0,1,2 in the
+// reference's order).  Frequency differences are shared between neighbouring tones and time
+// differences between consecutive steps, ~39 float64 adds per (column, f) instead of 150 per score.
+// Loads are coalesced (adjacent f = adjacent bins) and every value is fetched once per tone offset
+// from L1/L2; the spectrogram is read from HBM once.
+#include <cmath>
+
+#include "common.cuh"
+
+namespace ft8b {
+
+constexpr int kSyncThreads = 128;
+
+__device__ __constant__ int kCostas[7] = {3, 1, 4, 0, 6, 5, 2};  // ft8_decode.py:42
+
+struct SyncArgs {
+    const double *mag;   // [n_slots][T][F]
+    double *scores;      // [n_slots][nt][nf]
+    int T, F, s, b;      // time_osr = s, freq_osr = b
+    int nb;              // num_blocks = T / s                       (ftx_types.py:31-34)
+    int nu;              // candidates per phase = nb - 49 ; nt = nu*s
+    int nf;              // F - 7*b                                   (ft8_decode.py:109)
+};
+
+// number of comparisons ft8_sync_score makes for time index u (any phase): ft8_decode.py:62-94
+__device__ __forceinline__ int sync_num_comparisons(int u, int nb) {
+    int n = 0;
+    for (int m = 0; m < kNumSync; ++m)
+        for (int k = 0; k < kLenSync; ++k) {
+            const int g = u - 10 + m * kSyncOffset + k;
+            if (g < 0 || g >= nb) continue;
+            n += (kCostas[k] > 0) + 1 /* tone < 7 always */ + ((k > 0 && g > 0) ? 1 : 0) +
+                 ((k < kLenSync - 1 && g + 1 < nb) ? 1 : 0);
+        }
+    return n;
+}
+
+__global__ void __launch_bounds__(kSyncThreads) sync_scores_kernel(const SyncArgs a) {
+    extern __shared__ double sc[];            // [nu][kSyncThreads] running score sums, then int ncmp[nu]
+    const int tid = threadIdx.x;
+    const int f = blockIdx.x * kSyncThreads + tid;
+    const int rho = blockIdx.y;
+    const int64_t slot = blockIdx.z;
+    const int nb = a.nb, nu = a.nu, s = a.s, b = a.b;
+    const bool active = f < a.nf;
+
+    int *ncmp = reinterpret_cast<int *>(sc + (size_t)nu * kSyncThreads);   // comparisons per u
+    for (int u = tid; u < nu; u += kSyncThreads) ncmp[u] = sync_num_comparisons(u, nb);
+    for (int u = 0; u < nu; ++u) sc[u * kSyncThreads + tid] = 0.0;
+    __syncthreads();
+
+    const double *base = a.mag + slot * (int64_t)a.T * a.F + f;   // + col*F + tau*b
+
+    if (active) {
+        // register state: cur[tau] = A[g][f+tau*b], nxt[tau] = A[g+1][...]
+        double cur[8], nxt[8], dtprev[7], acc[7];
+#pragma unroll
+        for (int k = 0; k < 7; ++k) { dtprev[k] = 0.0; acc[k] = 0.0; }
+        {
+            const double *row = base + (int64_t)rho * a.F;   // g = 0 -> col = rho
+#pragma unroll
+            for (int tau = 0; tau < 8; ++tau) nxt[tau] = __ldg(row + tau * b);
+        }
+        for (int g = 0; g < nb; ++g) {
+#pragma unroll
+            for (int tau = 0; tau < 8; ++tau) cur[tau] = nxt[tau];
+            const bool has_next = (g + 1 < nb);
+            if (has_next) {
+                const double *row = base + (int64_t)(rho + s * (g + 1)) * a.F;
+#pragma unroll
+                for (int tau = 0; tau < 8; ++tau) nxt[tau] = __ldg(row + tau * b);
+            }
+            // dhi[tau] = A[tau] - A[tau+1]  (tau 0..6);  p - lo = -dhi[tau-1],  p - hi = dhi[tau]
+            double dhi[7], dt[7];
+#pragma unroll
+            for (int tau = 0; tau < 7; ++tau) dhi[tau] = __dsub_rn(cur[tau], cur[tau + 1]);
+            // dt[tau] = A[g][tau] - A[g+1][tau]  = (p - later);  (p - earlier) at g+1 is -dt[tau]
+#pragma unroll
+            for (int tau = 0; tau < 7; ++tau) dt[tau] = has_next ? __dsub_rn(cur[tau], nxt[tau]) : 0.0;
+            // cell sums G_k in the reference's order: (p-lo) + (p-hi) + (p-earlier) + (p-later)
+            double G[7];
+#pragma unroll
+            for (int k = 0; k < 7; ++k) {
+                const int tau = (k == 0) ? 3 : (k == 1) ? 1 : (k == 2) ? 4 : (k == 3) ? 0 : (k == 4) ? 6 : (k == 5) ? 5 : 2;
+                double v;
+                if (tau > 0) v = __dadd_rn(-dhi[tau - 1], dhi[tau]);     // ft8_decode.py:79-85
+                else v = dhi[0];
+                if (k > 0) v = __dadd_rn(v, dtprev[tau]);                // :88-90 (dtprev is 0 at g == 0)
+                if (k < 6) v = __dadd_rn(v, dt[tau]);                    // :92-94 (dt is 0 at g == nb-1)
+                G[k] = v;
+            }
+#pragma unroll
+            for (int tau = 0; tau < 7; ++tau) dtprev[tau] = -dt[tau];
+            // rotate the block accumulators: acc[k] holds S7(h = g-k) through cell k
+            const double done = __dadd_rn(acc[5], G[6]);
+#pragma unroll
+            for (int k = 5; k >= 1; --k) acc[k] = __dadd_rn(acc[k - 1], G[k]);
+            acc[0] = G[0];
+            // S7(h = g-6) is complete
+            {
+                const int h = g - 6;
+#pragma unroll
+                for (int m = 0; m < 3; ++m) {
+                    const int u = h + 10 - m * kSyncOffset;
+                    if (u >= 0 && u < nu) sc[u * kSyncThreads + tid] = __dadd_rn(sc[u * kSyncThreads + tid], done);
+                }
+            }
+        }
+        // flush partial blocks that run past the last symbol: h = nb-6 .. nb-1 (acc[5] .. acc[0])
+#pragma unroll
+        for (int k = 5; k >= 0; --k) {
+            const int h = nb - 1 - k;
+#pragma unroll
+            for (int m = 0; m < 3; ++m) {
+                const int u = h + 10 - m * kSyncOffset;
+                if (u >= 0 && u < nu) sc[u * kSyncThreads + tid] = __dadd_rn(sc[u * kSyncThreads + tid], acc[k]);
+            }
+        }
+        // normalise and store: score / num_comparisons, -inf when no comparison or non-finite (:97-100)
+        double *out = a.scores + slot * (int64_t)(nu * s) * a.nf + f;
+        for (int u = 0; u < nu; ++u) {
+            const int n = ncmp[u];
+            double v = sc[u * kSyncThreads + tid];
+            if (n == 0 || !isfinite(v)) v = -INFINITY;
+            else v = __ddiv_rn(v, (double)n);
+            out[(int64_t)(rho + s * u) * a.nf] = v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// S2b: selection.  One CTA per slot scans the score map in scan order (flat index = scan order).
+// ------------------------------------------------------------------------------------------
+constexpr int kSelThreads = 1024;
+constexpr int kSelPerThread = 4;   // consecutive scores per thread per chunk
+
+struct SelArgs {
+    const double *scores;   // [n_slots][L]
+    int64_t L;              // nt*nf
+    int nf, t0, K, Kpad;
+    double min_score;
+    int32_t *cand_time, *cand_freq, *n_cand, *n_pass;
+    double *cand_score;
+};
+
+__device__ __forceinline__ bool sel_pass(double v, double thr) {
+    // ft8_decode.py:127: skip if score == -inf or score < min_score
+    return (v != -INFINITY) && !(v < thr) && !isnan(v);
+}
+// ordering used for max/sort: higher score first, then earlier scan position
+__device__ __forceinline__ bool sel_better(double sa, long long ia, double sb, long long ib) {
+    return (sa > sb) || (sa == sb && ia < ib);
+}
+
+__global__ void __launch_bounds__(kSelThreads) select_candidates_kernel(const SelArgs a) {
+    extern __shared__ unsigned char sel_smem[];
+    double *hs = reinterpret_cast<double *>(sel_smem);                   // [Kpad] scores
+    long long *hi = reinterpret_cast<long long *>(hs + a.Kpad);          // [Kpad] scan indices
+    __shared__ int warp_cnt[32];
+    __shared__ int s_base, s_done;
+    __shared__ long long s_cut;
+    __shared__ double red_s[32];
+    __shared__ long long red_i[32];
+    __shared__ long long red_c[32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int64_t slot = blockIdx.x;
+    const double *sc = a.scores + slot * a.L;
+    const int K = a.K;
+
+    for (int i = tid; i < a.Kpad; i += kSelThreads) { hs[i] = -INFINITY; hi[i] = 0x7fffffffffffffffLL; }
+    if (tid == 0) { s_base = 0; s_done = 0; s_cut = -1; }
+    __syncthreads();
+
+    // ---- phase A: first K passers in scan order (ordered compaction) ----
+    const int64_t chunk = (int64_t)kSelThreads * kSelPerThread;
+    int64_t pos = 0;
+    long long total_pass = 0;   // only meaningful when the scan runs to the end (K never reached)
+    for (; pos < a.L; pos += chunk) {
+        const int64_t i0 = pos + (int64_t)tid * kSelPerThread;
+        double v[kSelPerThread];
+        int cnt = 0;
+#pragma unroll
+        for (int j = 0; j < kSelPerThread; ++j) {
+            v[j] = (i0 + j < a.L) ? __ldg(sc + i0 + j) : -INFINITY;
+            cnt += sel_pass(v[j], a.min_score) ? 1 : 0;
+        }
+        // exclusive prefix of cnt over the block (thread order = scan order)
+        int incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int n = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += n;
+        }
+        if (lane == 31) warp_cnt[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            int w = warp_cnt[lane];
+            int wi = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                int n = __shfl_up_sync(0xffffffffu, wi, d);
+                if (lane >= d) wi += n;
+            }
+            warp_cnt[lane] = wi - w;          // exclusive warp offsets
+            if (lane == 31) s_done = wi;      // chunk total (reuse s_done as scratch)
+        }
+        __syncthreads();
+        const int base = s_base;
+        int rank = base + warp_cnt[wid] + (incl - cnt);
+#pragma unroll
+        for (int j = 0; j < kSelPerThread; ++j) {
+            if (sel_pass(v[j], a.min_score)) {
+                if (rank < K) { hs[rank] = v[j]; hi[rank] = i0 + j; }
+                if (rank == K - 1) s_cut = i0 + j;
+                ++rank;
+            }
+        }
+        const int chunk_total = s_done;
+        __syncthreads();
+        if (tid == 0) s_base = base + chunk_total;
+        total_pass = (long long)base + chunk_total;
+        __syncthreads();
+        if (base + chunk_total >= K) { pos += chunk; break; }
+    }
+    const int n_first = (s_base < K) ? s_base : K;
+    const long long cut = s_cut;    // scan index of the K-th passer, -1 if fewer than K passers
+
+    // ---- phase B: running-record replacement over the passers after the K-th ----
+    long long n_pass_total = total_pass;
+    if (cut >= 0 && K > 0) {
+        double bs = -INFINITY;
+        long long bi = 0x7fffffffffffffffLL;
+        long long extra = 0;
+        for (int64_t i = cut + 1 + tid; i < a.L; i += kSelThreads) {
+            const double v = __ldg(sc + i);
+            if (sel_pass(v, a.min_score)) {
+                ++extra;
+                if (sel_better(v, i, bs, bi)) { bs = v; bi = i; }
+            }
+        }
+        // block arg-max (first occurrence on ties) and count
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+            const double os = __shfl_xor_sync(0xffffffffu, bs, d);
+            const long long oi = __shfl_xor_sync(0xffffffffu, bi, d);
+            extra += __shfl_xor_sync(0xffffffffu, extra, d);
+            if (sel_better(os, oi, bs, bi)) { bs = os; bi = oi; }
+        }
+        if (lane == 0) { red_s[wid] = bs; red_i[wid] = bi; red_c[wid] = extra; }
+        __syncthreads();
+        if (wid == 0) {
+            bs = red_s[lane]; bi = red_i[lane]; extra = red_c[lane];
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) {
+                const double os = __shfl_xor_sync(0xffffffffu, bs, d);
+                const long long oi = __shfl_xor_sync(0xffffffffu, bi, d);
+                extra += __shfl_xor_sync(0xffffffffu, extra, d);
+                if (sel_better(os, oi, bs, bi)) { bs = os; bi = oi; }
+            }
+            if (lane == 0) {
+                // b = best of H (heap root); replace when the later record is strictly greater (:136-137)
+                int best = 0;
+                for (int i = 1; i < n_first; ++i)
+                    if (sel_better(hs[i], hi[i], hs[best], hi[best])) best = i;
+                if (bs > hs[best]) { hs[best] = bs; hi[best] = bi; }
+                red_c[0] = extra;
+            }
+        }
+        __syncthreads();
+        // passers counted so far: everything up to and including the cut chunk is not fully counted;
+        // recompute as K-th passer rank (K) + later passers.
+        n_pass_total = (long long)K + red_c[0];
+    }
+    __syncthreads();
+
+    // ---- phase C: sort H by (score desc, scan index asc) - bitonic over Kpad ----
+    for (int size = 2; size <= a.Kpad; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = tid; i < a.Kpad; i += kSelThreads) {
+                const int j = i ^ stride;
+                if (j > i) {
+                    const bool up = ((i & size) == 0);   // "up" = better elements first
+                    const double si = hs[i], sj = hs[j];
+                    const long long ii = hi[i], ij = hi[j];
+                    const bool j_better = sel_better(sj, ij, si, ii);
+                    if (up ? j_better : !j_better) { hs[i] = sj; hs[j] = si; hi[i] = ij; hi[j] = ii; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = tid; i < K; i += kSelThreads) {
+        const int64_t o = slot * K + i;
+        if (i < n_first) {
+            a.cand_time[o] = a.t0 + (int)(hi[i] / a.nf);
+            a.cand_freq[o] = (int)(hi[i] % a.nf);
+            a.cand_score[o] = hs[i];
+        } else {
+            a.cand_time[o] = 0; a.cand_freq[o] = 0; a.cand_score[o] = 0.0;
+        }
+    }
+    if (tid == 0) {
+        a.n_cand[slot] = n_first;
+        if (a.n_pass) a.n_pass[slot] = (int32_t)(n_pass_total > 0x7fffffffLL ? 0x7fffffffLL : n_pass_total);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+int sync_scores(const double *mag, int64_t n_slots, int T, int F, int s, int b, double *scores, cudaStream_t stream) {
+    if (!mag || !scores) FT8B_ARG_FAIL("ft8b_sync_scores: null pointer");
+    if (T < 0 || F < 0 || s < 1 || b < 1) FT8B_ARG_FAIL("ft8b_sync_scores: bad shape");
+    int t0, nt, nf;
+    ft8b_search_ranges(T, F, s, b, &t0, &nt, &nf);
+    if (n_slots <= 0 || nt <= 0 || nf <= 0) return 0;
+    SyncArgs a;
+    a.mag = mag; a.scores = scores; a.T = T; a.F = F; a.s = s; a.b = b;
+    a.nb = T / s; a.nu = nt / s; a.nf = nf;
+    const size_t smem = sizeof(double) * (size_t)a.nu * kSyncThreads + sizeof(int) * (size_t)a.nu;
+    int dev = 0, max_smem = 0;
+    FT8B_CUDA_TRY(cudaGetDevice(&dev));
+    FT8B_CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    if (smem > (size_t)max_smem) {
+        set_error("ft8b_sync_scores: %d time offsets per phase need %zu bytes of shared memory (limit %d)", a.nu, smem, max_smem);
+        return FT8B_ERR_UNSUPPORTED;
+    }
+    if (s > 65535 || n_slots > 65535) {
+        set_error("ft8b_sync_scores: steps_per_symbol and slots per call must be <= 65535");
+        return FT8B_ERR_UNSUPPORTED;
+    }
+    FT8B_CUDA_TRY(cudaFuncSetAttribute(sync_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+    dim3 grid((nf + kSyncThreads - 1) / kSyncThreads, s, (unsigned)n_slots);
+    sync_scores_kernel<<<grid, kSyncThreads, smem, stream>>>(a);
+    FT8B_LAUNCH_CHECK("sync_scores_kernel");
+    return 0;
+}
+
+int select_candidates(const double *scores, int64_t n_slots, int nt, int nf, int t0, int K, double min_score,
+                      int32_t *cand_time, int32_t *cand_freq, double *cand_score, int32_t *n_cand, int32_t *n_pass,
+                      cudaStream_t stream) {
+    if (!cand_time || !cand_freq || !cand_score || !n_cand) FT8B_ARG_FAIL("ft8b_select_candidates: null pointer");
+    if (K < 0 || K > FT8B_MAX_CANDIDATES) {
+        set_error("ft8b_select_candidates: K=%d outside [0,%d]", K, FT8B_MAX_CANDIDATES);
+        return FT8B_ERR_UNSUPPORTED;
+    }
+    if (n_slots <= 0) return 0;
+    if (nt <= 0 || nf <= 0 || K == 0) {
+        FT8B_CUDA_TRY(cudaMemsetAsync(n_cand, 0, sizeof(int32_t) * n_slots, stream));
+        if (n_pass) FT8B_CUDA_TRY(cudaMemsetAsync(n_pass, 0, sizeof(int32_t) * n_slots, stream));
+        return 0;
+    }
+    if (!scores) FT8B_ARG_FAIL("ft8b_select_candidates: null scores");
+    SelArgs a;
+    a.scores = scores; a.L = (int64_t)nt * nf; a.nf = nf; a.t0 = t0; a.K = K;
+    int kp = 2;
+    while (kp < K) kp <<= 1;
+    a.Kpad = kp;
+    a.min_score = min_score;
+    a.cand_time = cand_time; a.cand_freq = cand_freq; a.cand_score = cand_score; a.n_cand = n_cand; a.n_pass = n_pass;
+    const size_t smem = (size_t)kp * (sizeof(double) + sizeof(long long));
+    FT8B_CUDA_TRY(cudaFuncSetAttribute(select_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem > 48 * 1024 ? (int)smem : 48 * 1024));
+    select_candidates_kernel<<<(unsigned)n_slots, kSelThreads, smem, stream>>>(a);
+    FT8B_LAUNCH_CHECK("select_candidates_kernel");
+    return 0;
+}
+
+}  // namespace ft8b

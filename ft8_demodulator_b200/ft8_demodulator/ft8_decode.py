@@ -1,0 +1,297 @@
+"""FT8 decode pipeline - the reference's `ft8_decode.py` API on the GPU.
+
+Every public function keeps the name, arguments and return value of
+`ft8_tools/ft8_demodulator/ft8_decode.py` (file:line cited per function); the arithmetic runs in the
+CUDA library (csrc/stft.cu, sync.cu, decode.cu) through the C ABI of include/ft8b200.h.
+`decode_slots` is the batched entry the reference lacks: same per-slot semantics,
+many equal-length slots per call.
+
+Deliberate differences: no printing, no PNG side effect; an input shorter
+than one analysis window returns [] (the reference raises IndexError although its own test expects
+[]); exact score ties, on which the reference raises TypeError, are ordered by scan position.
+"""
+from typing import List, Tuple
+
+import numpy as np
+import torch
+
+from .. import _lib, engine
+from .crc import compute_crc, extract_crc
+from .ftx_types import FT8Candidate, FT8DecodeStatus, FT8Message, FT8Protocol, FT8Waterfall  # noqa: F401
+from .ldpc_decoder import bp_decode  # noqa: F401  (the reference re-exports it from here)
+from .spectrogram_analyse import (FT8_SYMBOL_DURATION_S, FT8_SYMBOL_FREQ_INTERVAL_HZ,  # noqa: F401
+                                  _as_real_audio, calculate_spectrogram, time_axis)
+
+FT8_ND = 58
+FT8_NUM_SYNC = 3
+FT8_LENGTH_SYNC = 7
+FT8_SYNC_OFFSET = 36
+FT8_LDPC_N = 174
+FT8_LDPC_K = 91
+FT8_LDPC_K_BYTES = 12
+FT8_Gray_map = [0, 1, 3, 2, 5, 6, 4, 7]
+FT8_Costas_pattern = [3, 1, 4, 0, 6, 5, 2]
+
+
+# ------------------------------------------------------------------------------------------------
+# waterfall staging
+# ------------------------------------------------------------------------------------------------
+def _device_waterfall(wf: FT8Waterfall) -> torch.Tensor:
+    """[1, T, F] float64 device copy of wf.mag ([F, T] on the host), cached on the waterfall object.
+    The waterfall is treated as immutable once it has been handed to a GPU function."""
+    mag = wf.mag
+    key = (id(mag), mag.shape, mag.ctypes.data if isinstance(mag, np.ndarray) else 0, str(mag.dtype))
+    cached = wf.__dict__.get("_b200_dev")
+    if cached is not None and cached[0] == key:
+        return cached[1]
+    dev = engine.require_cuda()
+    host = np.ascontiguousarray(np.asarray(mag, dtype=np.float64).T)
+    t = engine._dev(host.reshape(1, host.shape[0], host.shape[1]), device=dev)
+    wf.__dict__["_b200_dev"] = (key, t)
+    wf.__dict__.pop("_b200_scores", None)
+    return t
+
+
+def _score_map(wf: FT8Waterfall):
+    cached = wf.__dict__.get("_b200_scores")
+    mag = _device_waterfall(wf)
+    if cached is None:
+        scores, t0 = engine.sync_scores(mag, wf.time_osr, wf.freq_osr)
+        cached = (scores, t0, None)
+        wf.__dict__["_b200_scores"] = cached
+    return cached
+
+
+# ------------------------------------------------------------------------------------------------
+# ft8_decode.py:47-149
+# ------------------------------------------------------------------------------------------------
+def ft8_sync_score(wf: FT8Waterfall, candidate: FT8Candidate) -> float:
+    """Costas sync score of one candidate (ft8_decode.py:47-100).  The whole score map of the waterfall
+    is computed on the GPU on first use and cached; positions outside ft8_find_candidates' search
+    range are not covered."""
+    scores, t0, host = _score_map(wf)
+    if host is None:
+        host = scores[0].cpu().numpy()
+        wf.__dict__["_b200_scores"] = (scores, t0, host)
+    ti = candidate.abs_time - t0
+    if not (0 <= ti < host.shape[0] and 0 <= candidate.abs_freq < host.shape[1]):
+        raise IndexError("candidate (%d, %d) is outside the candidate search range" % (candidate.abs_time,
+                                                                                     candidate.abs_freq))
+    return float(host[ti, candidate.abs_freq])
+
+
+def ft8_find_candidates(wf: FT8Waterfall, num_candidates: int, min_score: int) -> List[FT8Candidate]:
+    """Candidate search with the reference's exact selection semantics (ft8_decode.py:102-149)."""
+    scores, t0, _ = _score_map(wf)
+    ct, cf, cs, nc, _ = engine.select_candidates(scores, t0, int(num_candidates), float(min_score))
+    n = int(nc.cpu()[0])
+    ct, cf, cs = ct[0, :n].cpu().numpy(), cf[0, :n].cpu().numpy(), cs[0, :n].cpu().numpy()
+    return [FT8Candidate(waterfall=wf, abs_time=int(ct[i]), abs_freq=int(cf[i]), score=float(cs[i])) for i in range(n)]
+
+
+# ------------------------------------------------------------------------------------------------
+# ft8_decode.py:151-215
+# ------------------------------------------------------------------------------------------------
+def ft8_extract_symbol(wf: np.ndarray, logl: np.ndarray) -> None:
+    """Max-difference LLRs of one 8-FSK symbol (ft8_decode.py:151-161).  Host utility on 8 values; the
+    decode path does this inside csrc/decode.cu."""
+    s2 = [wf[g] for g in FT8_Gray_map]
+    logl[0] = max(s2[4], s2[5], s2[6], s2[7]) - max(s2[0], s2[1], s2[2], s2[3])
+    logl[1] = max(s2[2], s2[3], s2[6], s2[7]) - max(s2[0], s2[1], s2[4], s2[5])
+    logl[2] = max(s2[1], s2[3], s2[5], s2[7]) - max(s2[0], s2[2], s2[4], s2[6])
+
+
+def _cand_tensors(cand: FT8Candidate, dev):
+    ct = torch.tensor([[cand.abs_time]], dtype=torch.int32, device=dev)
+    cf = torch.tensor([[cand.abs_freq]], dtype=torch.int32, device=dev)
+    nc = torch.tensor([1], dtype=torch.int32, device=dev)
+    return ct, cf, nc
+
+
+def _check_candidate(wf: FT8Waterfall, cand: FT8Candidate) -> None:
+    if not (0 <= cand.abs_freq and cand.abs_freq + 7 * wf.freq_osr < wf.mag.shape[0]):
+        raise IndexError("candidate frequency outside the waterfall")
+
+
+def ft8_extract_likelihood(wf: FT8Waterfall, cand: FT8Candidate, log174: np.ndarray) -> None:
+    """174 un-normalised LLRs written into log174 (ft8_decode.py:164-188)."""
+    _check_candidate(wf, cand)
+    mag = _device_waterfall(wf)
+    ct, cf, nc = _cand_tensors(cand, mag.device)
+    log174[:FT8_LDPC_N] = engine.extract_llr(mag, wf.time_osr, wf.freq_osr, ct, cf, nc, normalize=False)[0, 0].cpu().numpy()
+
+
+def ftx_normalize_logl(log174: np.ndarray) -> None:
+    """Scale log174 in place to variance 24 (ft8_decode.py:190-198)."""
+    dev = engine.require_cuda()
+    t = engine._dev(np.asarray(log174, dtype=np.float64).reshape(1, FT8_LDPC_N).copy(), device=dev)
+    log174[:FT8_LDPC_N] = engine.normalize_llr_(t)[0].cpu().numpy()
+
+
+def pack_bits(bit_array: np.ndarray, num_bits: int) -> bytearray:
+    """MSB-first bit packing (ft8_decode.py:200-215); host byte utility."""
+    bits = (np.asarray(bit_array).reshape(-1)[:num_bits] != 0).astype(np.uint8)
+    return bytearray(np.packbits(bits).tobytes())
+
+
+def ftx_compute_crc(data: bytearray, num_bits: int) -> int:
+    return compute_crc(data, num_bits)
+
+
+def ftx_extract_crc(data: bytearray) -> int:
+    return extract_crc(data)
+
+
+# ------------------------------------------------------------------------------------------------
+# ft8_decode.py:225-286
+# ------------------------------------------------------------------------------------------------
+def ft8_decode_candidate(wf: FT8Waterfall, cand: FT8Candidate, max_iterations: int
+                         ) -> Tuple[bool, FT8Message, FT8DecodeStatus]:
+    """LLR extraction + LDPC + CRC for one candidate (ft8_decode.py:225-273)."""
+    _check_candidate(wf, cand)
+    mag = _device_waterfall(wf)
+    ct, cf, nc = _cand_tensors(cand, mag.device)
+    d = engine.decode_candidates(mag, wf.time_osr, wf.freq_osr, ct, cf, nc, int(max_iterations))
+    message, status = FT8Message(), FT8DecodeStatus()
+    status.ldpc_errors = int(d.ldpc_errors.cpu()[0, 0])
+    status.crc_extracted = int(d.crc_extracted.cpu()[0, 0])
+    status.crc_calculated = int(d.crc_calculated.cpu()[0, 0])
+    ok = bool(d.ok.cpu()[0, 0])
+    if ok:
+        message.hash = status.crc_calculated
+        message.payload = bytearray(d.payload[0, 0].cpu().numpy().tobytes())
+    return ok, message, status
+
+
+def create_waterfall_from_spectrogram(spectrogram: np.ndarray, time_osr: int, freq_osr: int) -> FT8Waterfall:
+    """Wrap a [frequency, time] spectrogram (ft8_decode.py:275-286)."""
+    if len(spectrogram.shape) != 2:
+        raise ValueError("spectrogram must be a 2D array with shape (frequency, time)")
+    return FT8Waterfall(mag=spectrogram, time_osr=time_osr, freq_osr=freq_osr)
+
+
+# ------------------------------------------------------------------------------------------------
+# ft8_decode.py:288-394 and the batched form
+# ------------------------------------------------------------------------------------------------
+def decode_geometry(n_samples: int, sample_rate, bins_per_tone: int, steps_per_symbol: int, freq_min=None,
+                    freq_max=None, time_min=None, time_max=None):
+    """Host-side index arithmetic of decode_ft8_message: window geometry and the inclusive frequency /
+    time masks of ft8_decode.py:323-341 turned into contiguous [lo, hi) ranges.
+    Returns dict(nperseg, hop, nfft, T_all, bin_lo, bin_hi, frame_lo, frame_hi)."""
+    nperseg, hop, nfft = _lib.plan(sample_rate, bins_per_tone, steps_per_symbol)
+    T_all = _lib.num_frames(n_samples, nperseg, hop)
+    n_pos = (nfft - 1) // 2 + 1
+    bin_lo, bin_hi = 0, n_pos
+    if freq_min is not None or freq_max is not None:
+        f = np.fft.fftfreq(nfft, 1 / sample_rate)[:n_pos]          # the f >= 0 rows, NumPy's rounding
+        fmin = freq_min if freq_min is not None else f[0]
+        fmax = freq_max if freq_max is not None else f[-1]
+        idx = np.nonzero((f >= fmin) & (f <= fmax))[0]
+        bin_lo, bin_hi = (int(idx[0]), int(idx[-1]) + 1) if len(idx) else (0, 0)
+    frame_lo, frame_hi = 0, T_all
+    if T_all > 0 and (time_min is not None or time_max is not None):
+        t = time_axis(n_samples, nperseg, hop, sample_rate)
+        tmin = time_min if time_min is not None else t[0]
+        tmax = time_max if time_max is not None else t[-1]
+        idx = np.nonzero((t >= tmin) & (t <= tmax))[0]
+        frame_lo, frame_hi = (int(idx[0]), int(idx[-1]) + 1) if len(idx) else (0, 0)
+    return dict(nperseg=nperseg, hop=hop, nfft=nfft, T_all=T_all, bin_lo=bin_lo, bin_hi=bin_hi, frame_lo=frame_lo,
+                frame_hi=frame_hi)
+
+
+def _results_from_arrays(out, slot: int, sample_rate, freq_osr: int) -> list:
+    """The reference's return list for one slot: successes in candidate order, 5-tuples (ft8_decode.py:383-391)."""
+    res = []
+    n = int(out.n_cand[slot])
+    for c in range(n):
+        if not out.ok[slot, c]:
+            continue
+        crc = int(out.crc_calculated[slot, c])
+        msg = FT8Message(payload=bytearray(out.payload[slot, c].numpy().tobytes()), hash=crc)
+        st = FT8DecodeStatus(ldpc_errors=int(out.ldpc_errors[slot, c]), crc_extracted=int(out.crc_extracted[slot, c]),
+                             crc_calculated=crc)
+        abs_time, abs_freq = int(out.cand_time[slot, c]), int(out.cand_freq[slot, c])
+        res.append((msg, st, abs_time / sample_rate, (abs_freq / freq_osr) * FT8_SYMBOL_FREQ_INTERVAL_HZ,
+                    float(out.cand_score[slot, c])))
+    return res
+
+
+class BatchDecodes:
+    """Host-side result of decode_slots: packed arrays plus lazy per-slot materialisation."""
+
+    def __init__(self, arrays: engine.SlotDecodes, sample_rate, freq_osr: int):
+        self.arrays, self.sample_rate, self.freq_osr = arrays, sample_rate, freq_osr
+
+    def __len__(self):
+        return self.arrays.n_cand.shape[0]
+
+    def __getitem__(self, slot: int) -> list:
+        return _results_from_arrays(self.arrays, slot, self.sample_rate, self.freq_osr)
+
+    def to_lists(self) -> list:
+        return [self[i] for i in range(len(self))]
+
+    def payload_sets(self) -> list:
+        """Per slot: set of decoded payloads (bytes)."""
+        a = self.arrays
+        ok = a.ok.numpy().astype(bool)
+        pl = a.payload.numpy()
+        return [set(bytes(pl[i, c]) for c in np.nonzero(ok[i])[0]) for i in range(len(self))]
+
+
+def decode_slots(waves, sample_rate, bins_per_tone: int = 2, steps_per_symbol: int = 2, max_candidates: int = 20,
+                 min_score=10, max_iterations: int = 20, freq_min=None, freq_max=None, time_min=None, time_max=None,
+                 chunk_slots: int = 0, return_device: bool = False):
+    """Decode a batch of equal-length slots: waves [B, N] (NumPy or torch, host or device, float32/float64).
+
+    Per-slot semantics are exactly decode_ft8_message's.  Host input is copied to the GPU inside this
+    call (pinned torch tensors copy asynchronously); results come back as a BatchDecodes (host) or, with
+    return_device=True, as the engine.SlotDecodes device tensors."""
+    dev = engine.require_cuda()
+    if isinstance(waves, np.ndarray):
+        if np.iscomplexobj(waves):
+            raise NotImplementedError("complex input is not covered by the CUDA STFT yet (real audio only)")
+        if waves.dtype not in (np.float32, np.float64):
+            waves = waves.astype(np.float64)
+        waves = torch.from_numpy(np.ascontiguousarray(waves))
+    if waves.dim() == 1:
+        waves = waves.reshape(1, -1)
+    if waves.dtype not in (torch.float32, torch.float64):
+        waves = waves.to(torch.float64)
+    B, N = waves.shape
+    g = decode_geometry(N, sample_rate, bins_per_tone, steps_per_symbol, freq_min, freq_max, time_min, time_max)
+    params = engine.make_params(sample_rate, bins_per_tone, steps_per_symbol, max_candidates, min_score, max_iterations,
+                                g["bin_lo"], g["bin_hi"], g["frame_lo"], g["frame_hi"], chunk_slots)
+    dec = engine.SlotDecoder(B, N, params, device=dev)
+    if B and g["T_all"] > 0:
+        wdev = waves if waves.is_cuda else waves.to(dev, non_blocking=True)
+        if wdev.stride(1) != 1:
+            wdev = wdev.contiguous()
+        dec.run(wdev)
+    out = dec.out
+    if return_device:
+        return out
+    return BatchDecodes(out.cpu(), sample_rate, bins_per_tone)
+
+
+def decode_ft8_message(wave_data: np.ndarray, sample_rate: int, bins_per_tone: int = 2, steps_per_symbol: int = 2,
+                       max_candidates: int = 20, min_score: int = 10, max_iterations: int = 20,
+                       freq_min: float = None, freq_max: float = None, time_min: float = None, time_max: float = None
+                       ) -> List[Tuple[FT8Message, FT8DecodeStatus, float, float, float]]:
+    """Decode one waveform (ft8_decode.py:288-394).  Returns the reference's list of
+    (FT8Message, FT8DecodeStatus, time_sec, freq_hz, score) in candidate (score-descending) order, with
+    time_sec = abs_time / sample_rate and freq_hz = abs_freq / bins_per_tone * 6.25 as the reference defines them."""
+    x = _as_real_audio(wave_data)
+    nperseg, _, _ = _lib.plan(sample_rate, bins_per_tone, steps_per_symbol)
+    if len(x) < nperseg:
+        return []
+    return decode_slots(x.reshape(1, -1), sample_rate, bins_per_tone, steps_per_symbol, max_candidates, min_score,
+                        max_iterations, freq_min, freq_max, time_min, time_max)[0]
+
+
+__all__ = [
+    "ft8_sync_score", "ft8_find_candidates", "ft8_extract_symbol", "ft8_extract_likelihood", "ftx_normalize_logl",
+    "pack_bits", "ftx_compute_crc", "ftx_extract_crc", "ft8_decode_candidate", "create_waterfall_from_spectrogram",
+    "decode_ft8_message", "decode_slots", "decode_geometry", "BatchDecodes", "FT8Waterfall", "FT8Candidate",
+    "FT8Message", "FT8DecodeStatus", "FT8Protocol", "bp_decode", "calculate_spectrogram",
+]

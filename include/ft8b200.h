@@ -1,0 +1,162 @@
+/*
+ * ft8b200.h - C ABI of libft8b200.so, the B200 (sm_100a) FT8 demodulation hot path.
+ *
+ * The reference (Rintazero/ft8_demodulator) is pure Python and has no FFI; its "operator
+ * interface" for this path is the set of Python functions in src/ft8_tools/ft8_demodulator/.
+ * Each entry point below replaces the arithmetic of the reference function(s) it cites; the
+ * Python mirror in ft8_demodulator_b200/ft8_demodulator/ binds them with ctypes and keeps the
+ * reference's names, argument meaning and error behaviour.
+ *
+ * Conventions
+ *   - return 0 = OK, negative = argument / capability error (FT8B_ERR_*), positive = cudaError_t;
+ *     ft8b_last_error() returns a thread-local description of the last failure.
+ *   - every data pointer is a DEVICE pointer owned by the caller (contiguous, 16-byte aligned);
+ *     the library allocates nothing per call.  Per-(device, nfft) window/twiddle tables are
+ *     created on first use (mutex-guarded, synchronous) and live until ft8b_release().
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); every call is
+ *     asynchronous on it.
+ *   - arithmetic is IEEE float64 throughout ("f64"): the reference computes in float64 for
+ *     float64 audio, and bit-exact candidate/bit/payload parity needs it.  float32 audio is
+ *     widened on load (exact).
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails.
+ *
+ * Layouts (row-major, last index fastest)
+ *   wave    [n_slots][slot_stride]            float32 or float64 samples, n_samples used per slot
+ *   mag     [n_slots][T][F]                   dB spectrogram, time-major (the reference's
+ *                                             FT8Waterfall.mag is [F][T]; the Python mirror transposes)
+ *   scores  [n_slots][nt][nf]                 Costas sync scores in the reference's scan order
+ *   cand_*  [n_slots][K]                      candidates, score-descending; n_cand[n_slots]
+ *   llr     [n_words][174], plain [n_words][174] (one byte per bit), payload [n_words][10]
+ */
+#ifndef FT8B200_H
+#define FT8B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FT8B_VERSION 100
+
+#define FT8B_ERR_ARG (-1)          /* bad argument */
+#define FT8B_ERR_UNSUPPORTED (-2)  /* size outside what the kernels cover (see message) */
+#define FT8B_ERR_NO_DEVICE (-3)    /* no CUDA device / driver */
+
+#define FT8B_DTYPE_F32 0
+#define FT8B_DTYPE_F64 1
+
+#define FT8B_LDPC_N 174
+#define FT8B_LDPC_M 83
+#define FT8B_MAX_CANDIDATES 4096   /* K limit of ft8b_select_candidates */
+
+int ft8b_version(void);
+const char *ft8b_last_error(void);
+/* Free the cached per-device tables (optional; for tests / orderly shutdown). */
+int ft8b_release(void);
+
+/* Window/FFT geometry of calculate_spectrogram (spectrogram_analyse.py:32-43):
+ * nperseg = int(0.16*fs), hop = nperseg - noverlap, nfft = int(fs/6.25*bins_per_tone). Host only. */
+int ft8b_plan(double sample_rate, int bins_per_tone, int steps_per_symbol, int *nperseg, int *hop, int *nfft);
+/* Frames scipy produces: (n - nperseg)/hop + 1, or 0 when n < nperseg (spectrogram_analyse.py:37-39). */
+int64_t ft8b_num_frames(int64_t n_samples, int nperseg, int hop);
+/* Candidate search ranges of ft8_find_candidates (ft8_decode.py:108-109):
+ * abs_time in [t0, t0+nt), abs_freq in [0, nf).  nt or nf <= 0 means "no candidates". */
+int ft8b_search_ranges(int T, int F, int time_osr, int freq_osr, int *t0, int *nt, int *nf);
+
+/*
+ * S1  calculate_spectrogram (spectrogram_analyse.py:19-66 -> scipy.signal.spectrogram, window='hann',
+ *     detrend=False, return_onesided=False, scaling='spectrum') fused with the 10*log10(1e-12+|S|) of
+ *     :59-60 and with the row/column selection of decode_ft8_message (ft8_decode.py:323-341).
+ *     Real input; writes bins [bin_lo, bin_hi) of 0..floor(nfft/2) and frames [frame_lo, frame_hi) as
+ *     mag[slot][frame-frame_lo][bin-bin_lo].  The two-sided fftshifted array the reference returns
+ *     is the mirror image of these rows (the Python mirror builds it).
+ */
+int ft8b_stft_db(const void *wave, int wave_dtype, int64_t n_slots, int64_t n_samples, int64_t slot_stride,
+                 int nperseg, int hop, int nfft, int bin_lo, int bin_hi, int64_t frame_lo, int64_t frame_hi,
+                 double *mag, void *stream);
+
+/*
+ * S2a ft8_sync_score for every (abs_time, abs_freq) of ft8_find_candidates' double loop
+ *     (ft8_decode.py:47-100, 108-124).  scores[slot][abs_time - t0][abs_freq]; -inf where the
+ *     reference returns -inf.
+ */
+int ft8b_sync_scores(const double *mag, int64_t n_slots, int T, int F, int time_osr, int freq_osr, double *scores,
+                     void *stream);
+
+/*
+ * S2b Candidate selection with the reference's exact heap semantics (ft8_decode.py:127-140):
+ *     the first K threshold passers in scan order, the running best replaced by every later
+ *     strictly greater score, result sorted by descending score.  K <= FT8B_MAX_CANDIDATES.
+ *     Exact score ties (the reference raises TypeError) are ordered by scan position.
+ *     n_pass (optional, may be NULL) receives the number of threshold passers per slot.
+ */
+int ft8b_select_candidates(const double *scores, int64_t n_slots, int nt, int nf, int t0, int K, double min_score,
+                           int32_t *cand_time, int32_t *cand_freq, double *cand_score, int32_t *n_cand,
+                           int32_t *n_pass, void *stream);
+
+/*
+ * S3  ft8_decode_candidate (ft8_decode.py:225-273) for every candidate of every slot:
+ *     ft8_extract_likelihood (:164-188) + ftx_normalize_logl (:190-198) + bp_decode
+ *     (ldpc_decoder.py:54-113, sum-product with the rational tanh/atanh of :11-31) + pack_bits (:200-215)
+ *     + CRC-14 (crc.py:11-54).  One warp per candidate.  Entries c >= n_cand[slot] are zero-filled.
+ *     Outputs are [n_slots][K](x...); llr_out and plain_out may be NULL.
+ */
+int ft8b_decode_candidates(const double *mag, int64_t n_slots, int T, int F, int time_osr, int freq_osr,
+                           const int32_t *cand_time, const int32_t *cand_freq, const int32_t *n_cand, int K,
+                           int max_iterations, uint8_t *ok, int32_t *ldpc_errors, int32_t *crc_extracted,
+                           int32_t *crc_calculated, uint8_t *payload, double *llr_out, uint8_t *plain_out,
+                           void *stream);
+
+/*
+ * S3' bp_decode + CRC check on caller-supplied, already normalised LLR vectors
+ *     (ldpc_decoder.py:54-113; ft8_decode.py:236-271).  plain/min_errors are what bp_decode returns;
+ *     the CRC fields follow ft8_decode_candidate (zero unless min_errors == 0).  plain, ldpc_errors and
+ *     ok are required; the other outputs may be NULL.
+ */
+int ft8b_ldpc_crc(const double *llr, int64_t n_words, int max_iterations, uint8_t *plain, int32_t *ldpc_errors,
+                  int32_t *crc_extracted, int32_t *crc_calculated, uint8_t *payload, uint8_t *ok, void *stream);
+
+/*
+ * ft8_extract_likelihood (ft8_decode.py:164-188), optionally followed by ftx_normalize_logl (:190-198),
+ * for every candidate: llr[n_slots][K][174].  scratch_u8 / scratch_i32 are [n_slots][K] work arrays.
+ */
+int ft8b_extract_llr(const double *mag, int64_t n_slots, int T, int F, int time_osr, int freq_osr,
+                     const int32_t *cand_time, const int32_t *cand_freq, const int32_t *n_cand, int K, int normalize,
+                     double *llr, uint8_t *scratch_u8, int32_t *scratch_i32, void *stream);
+/* ftx_normalize_logl (ft8_decode.py:190-198) in place on llr[n_words][174]. */
+int ft8b_normalize_llr(double *llr, int64_t n_words, void *stream);
+/* ldpc_check (ldpc_decoder.py:33-52): errors[w] = unsatisfied parity checks of bits[w][174] (one byte per bit). */
+int ft8b_ldpc_check(const uint8_t *bits, int64_t n_words, int32_t *errors, void *stream);
+
+/*
+ * Whole path, decode_ft8_message (ft8_decode.py:288-394) for a batch of equal-length slots:
+ * S1 -> S2a -> S2b -> S3 in chunks of `chunk_slots` slots so the float64 spectrogram and score map of a
+ * chunk stay L2-resident between kernels.  `workspace` must hold ft8b_decode_workspace_bytes() bytes.
+ * Outputs as in ft8b_select_candidates / ft8b_decode_candidates ([n_slots][K]...).
+ */
+typedef struct {
+    double sample_rate;
+    int32_t bins_per_tone, steps_per_symbol;
+    int32_t max_candidates;
+    int32_t max_iterations;
+    double min_score;
+    int32_t bin_lo, bin_hi;       /* rows kept (freq_min/freq_max mask), within [0, ceil(nfft/2)] */
+    int64_t frame_lo, frame_hi;   /* columns kept (time_min/time_max mask) */
+    int32_t chunk_slots;          /* 0 = library default */
+    int32_t reserved;
+} ft8b_decode_params;
+
+int64_t ft8b_decode_workspace_bytes(const ft8b_decode_params *p, int64_t n_slots, int64_t n_samples);
+int ft8b_decode_slots(const void *wave, int wave_dtype, int64_t n_slots, int64_t n_samples, int64_t slot_stride,
+                      const ft8b_decode_params *p, void *workspace, int64_t workspace_bytes, int32_t *cand_time,
+                      int32_t *cand_freq, double *cand_score, int32_t *n_cand, uint8_t *ok, int32_t *ldpc_errors,
+                      int32_t *crc_extracted, int32_t *crc_calculated, uint8_t *payload, void *stream);
+
+/* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
+int64_t ft8b_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FT8B200_H */
