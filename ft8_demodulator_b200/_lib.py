@@ -34,6 +34,8 @@ SIGNATURES = {
     "ft8b_last_error": (C.c_char_p, []),
     "ft8b_release": (_i, []),
     "ft8b_launch_count": (_i64, []),
+    "ft8b_stage_timing": (_i, [_i]),
+    "ft8b_stage_times": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "ft8b_plan": (_i, [_d, _i, _i, _ip, _ip, _ip]),
     "ft8b_num_frames": (_i64, [_i64, _i, _i]),
     "ft8b_search_ranges": (_i, [_i, _i, _i, _i, _ip, _ip, _ip]),

@@ -2,6 +2,7 @@
 #include <cmath>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 #include "common.cuh"
 
@@ -29,11 +30,50 @@ int ldpc_crc(const double *, int64_t, int, uint8_t *, int32_t *, int32_t *, int3
 int extract_llr(const double *, int64_t, int, int, int, int, const int32_t *, const int32_t *, const int32_t *, int, int,
                 double *, uint8_t *, int32_t *, cudaStream_t);
 int normalize_llr(double *, int64_t, cudaStream_t);
+int ldpc_crc_masked(const double *, const int32_t *, int, int64_t, int, uint8_t *, int32_t *, int32_t *, int32_t *, uint8_t *,
+                    cudaStream_t);
 int ldpc_check(const uint8_t *, int64_t, int32_t *, cudaStream_t);
 
+// ---- optional per-stage timing (cudaEvent pairs on the launching stream), used by bench.py ----
+constexpr int kStages = 5;   // stft, sync, select, llr, ldpc
+struct StageTimer {
+    std::mutex mu;
+    bool enabled = false;
+    std::vector<cudaEvent_t> beg[kStages], end[kStages];
+    size_t used[kStages] = {0, 0, 0, 0, 0};
+    double ms[kStages] = {0, 0, 0, 0, 0};
+    int64_t launches[kStages] = {0, 0, 0, 0, 0};
+};
+static StageTimer g_timer;
+
+struct StageScope {
+    int stage;
+    cudaStream_t stream;
+    cudaEvent_t e_end = nullptr;
+    StageScope(int st, cudaStream_t s) : stage(st), stream(s) {
+        if (!g_timer.enabled) return;
+        std::lock_guard<std::mutex> lk(g_timer.mu);
+        size_t &u = g_timer.used[stage];
+        if (u == g_timer.beg[stage].size()) {
+            cudaEvent_t a, b;
+            cudaEventCreate(&a);
+            cudaEventCreate(&b);
+            g_timer.beg[stage].push_back(a);
+            g_timer.end[stage].push_back(b);
+        }
+        cudaEventRecord(g_timer.beg[stage][u], stream);
+        e_end = g_timer.end[stage][u];
+        ++u;
+    }
+    ~StageScope() {
+        if (e_end) cudaEventRecord(e_end, stream);
+    }
+};
+
 static int default_chunk_slots(int64_t per_slot_bytes) {
-    // keep the chunk's float64 spectrogram + score map around half of B200's ~126 MB L2
-    int64_t c = (64ll << 20) / (per_slot_bytes > 0 ? per_slot_bytes : 1);
+    // Enough slots per launch to fill 148 SMs several times over in every stage; the kernels are bound by
+    // the FP64 pipe, not HBM, so L2 residency of the chunk's spectrogram is secondary.
+    int64_t c = (512ll << 20) / (per_slot_bytes > 0 ? per_slot_bytes : 1);
     if (c < 1) c = 1;
     if (c > 4096) c = 4096;
     return (int)c;
@@ -70,6 +110,31 @@ int ft8b_version(void) { return FT8B_VERSION; }
 const char *ft8b_last_error(void) { return g_err; }
 int ft8b_release(void) { return release_plans(); }
 int64_t ft8b_launch_count(void) { return g_launches.load(); }
+
+int ft8b_stage_timing(int enable) {
+    std::lock_guard<std::mutex> lk(g_timer.mu);
+    g_timer.enabled = enable != 0;
+    for (int s = 0; s < kStages; ++s) { g_timer.used[s] = 0; g_timer.ms[s] = 0; g_timer.launches[s] = 0; }
+    return 0;
+}
+
+int ft8b_stage_times(double *ms, int64_t *launches) {
+    if (!ms || !launches) FT8B_ARG_FAIL("ft8b_stage_times: null pointer");
+    std::lock_guard<std::mutex> lk(g_timer.mu);
+    for (int s = 0; s < kStages; ++s) {
+        for (size_t i = 0; i < g_timer.used[s]; ++i) {
+            FT8B_CUDA_TRY(cudaEventSynchronize(g_timer.end[s][i]));
+            float t = 0.f;
+            FT8B_CUDA_TRY(cudaEventElapsedTime(&t, g_timer.beg[s][i], g_timer.end[s][i]));
+            g_timer.ms[s] += t;
+            g_timer.launches[s] += 1;
+        }
+        g_timer.used[s] = 0;
+        ms[s] = g_timer.ms[s];
+        launches[s] = g_timer.launches[s];
+    }
+    return 0;
+}
 
 int ft8b_plan(double fs, int bins_per_tone, int steps_per_symbol, int *nperseg, int *hop, int *nfft) {
     if (!nperseg || !hop || !nfft || bins_per_tone < 1 || steps_per_symbol < 1 || !(fs > 0)) FT8B_ARG_FAIL("ft8b_plan: bad argument");
@@ -148,7 +213,8 @@ int64_t ft8b_decode_workspace_bytes(const ft8b_decode_params *p, int64_t n_slots
     const int64_t per_slot = 8 * (g.mag_elems + g.score_elems);
     int chunk = p->chunk_slots > 0 ? p->chunk_slots : default_chunk_slots(per_slot);
     if (chunk > n_slots) chunk = (int)(n_slots > 0 ? n_slots : 1);
-    return per_slot * chunk + 256;
+    // chunk spectrogram + score map, then the LLR vectors of every candidate of the batch
+    return per_slot * chunk + 8ll * kLdpcN * p->max_candidates * (n_slots > 0 ? n_slots : 0) + 256;
 }
 
 int ft8b_decode_slots(const void *wave, int wave_dtype, int64_t n_slots, int64_t n_samples, int64_t slot_stride,
@@ -181,27 +247,47 @@ int ft8b_decode_slots(const void *wave, int wave_dtype, int64_t n_slots, int64_t
     }
     int chunk = p->chunk_slots > 0 ? p->chunk_slots : default_chunk_slots(per_slot);
     if (chunk > n_slots) chunk = (int)n_slots;
-    if (workspace_bytes < per_slot * chunk) FT8B_ARG_FAIL("ft8b_decode_slots: workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)(per_slot * chunk));
+    const int64_t need = per_slot * chunk + 8ll * kLdpcN * K * n_slots;
+    if (workspace_bytes < need) FT8B_ARG_FAIL("ft8b_decode_slots: workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)need);
     double *mag = reinterpret_cast<double *>(workspace);
     double *scores = mag + g.mag_elems * chunk;
+    double *llr = scores + g.score_elems * chunk;   // [n_slots][K][174]
     for (int64_t s0 = 0; s0 < n_slots; s0 += chunk) {
         const int64_t nb = (n_slots - s0 < chunk) ? (n_slots - s0) : chunk;
         const char *w = reinterpret_cast<const char *>(wave) + (size_t)s0 * slot_stride * elt;
-        rc = stft_db(w, wave_dtype, nb, n_samples, slot_stride, g.nperseg, g.hop, g.nfft, p->bin_lo, p->bin_hi, p->frame_lo,
-                     p->frame_hi, mag, stream);
+        {
+            StageScope t(0, stream);
+            rc = stft_db(w, wave_dtype, nb, n_samples, slot_stride, g.nperseg, g.hop, g.nfft, p->bin_lo, p->bin_hi,
+                         p->frame_lo, p->frame_hi, mag, stream);
+        }
         if (rc) return rc;
-        rc = sync_scores(mag, nb, (int)g.T, g.F, p->steps_per_symbol, p->bins_per_tone, scores, stream);
+        {
+            StageScope t(1, stream);
+            rc = sync_scores(mag, nb, (int)g.T, g.F, p->steps_per_symbol, p->bins_per_tone, scores, stream);
+        }
         if (rc) return rc;
-        rc = select_candidates(scores, nb, g.nt, g.nf, g.t0, K, p->min_score, cand_time + s0 * K, cand_freq + s0 * K,
-                               cand_score + s0 * K, n_cand + s0, nullptr, stream);
+        {
+            StageScope t(2, stream);
+            rc = select_candidates(scores, nb, g.nt, g.nf, g.t0, K, p->min_score, cand_time + s0 * K, cand_freq + s0 * K,
+                                   cand_score + s0 * K, n_cand + s0, nullptr, stream);
+        }
         if (rc) return rc;
-        rc = decode_candidates(mag, nb, (int)g.T, g.F, p->steps_per_symbol, p->bins_per_tone, cand_time + s0 * K,
-                               cand_freq + s0 * K, n_cand + s0, K, p->max_iterations, ok + s0 * K, ldpc_errors + s0 * K,
-                               crc_extracted ? crc_extracted + s0 * K : nullptr,
-                               crc_calculated ? crc_calculated + s0 * K : nullptr, payload + s0 * K * 10, nullptr, nullptr,
-                               stream);
+        {
+            // LLRs of this chunk's candidates while its spectrogram is still in L2; ok/ldpc_errors serve as scratch
+            StageScope t(3, stream);
+            rc = extract_llr(mag, nb, (int)g.T, g.F, p->steps_per_symbol, p->bins_per_tone, cand_time + s0 * K,
+                             cand_freq + s0 * K, n_cand + s0, K, 1, llr + s0 * K * kLdpcN, ok + s0 * K, ldpc_errors + s0 * K,
+                             stream);
+        }
         if (rc) return rc;
     }
+    {
+        // one launch over every candidate of the batch: warps stay busy although iteration counts differ
+        StageScope t(4, stream);
+        rc = ldpc_crc_masked(llr, n_cand, K, n_slots * (int64_t)K, p->max_iterations, ok, ldpc_errors, crc_extracted,
+                             crc_calculated, payload, stream);
+    }
+    if (rc) return rc;
     return 0;
 }
 

@@ -12,11 +12,13 @@
 // Hann window, power scaling, +1e-12, log10 and the band/time crop are fused into the load and the
 // store, so HBM sees each audio sample ~once (the hop overlap is served by L2) and each dB value once.
 #include <cmath>
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <vector>
 
 #include "common.cuh"
+#include "stft1920.cuh"
 
 namespace ft8b {
 
@@ -33,6 +35,9 @@ struct StftPlan {
     double scale = 0.0;         // 1/(sum win)^2
     int nthreads = 0;
     size_t smem = 0;
+    // canonical-geometry fast path (nperseg 1920, nfft 3840): extra twiddle tables for stft1920_kernel
+    int fast = 0;
+    double2 *tw2 = nullptr, *tw3 = nullptr;
 };
 
 struct StftArgs {
@@ -322,6 +327,24 @@ static int get_plan(int nperseg, int nfft, const StftPlan **out) {
     FT8B_CUDA_TRY(cudaFuncSetAttribute(stft_db_kernel<double, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     FT8B_CUDA_TRY(cudaFuncSetAttribute(stft_db_kernel<float, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     FT8B_CUDA_TRY(cudaFuncSetAttribute(stft_db_kernel<double, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    if (nperseg == 1920 && nfft == 3840) {
+        std::vector<double2> t2(16 * 15), t3(8 * 240);
+        for (int t = 0; t < 16; ++t)
+            for (int k = 0; k < 15; ++k) {
+                long double ang = -two_pi * (long double)(t * k) / 240.0L;
+                t2[t * 15 + k] = make_double2((double)cosl(ang), (double)sinl(ang));
+            }
+        for (int t = 0; t < 8; ++t)
+            for (int j = 0; j < 240; ++j) {
+                long double ang = -two_pi * (long double)(t * j) / 1920.0L;
+                t3[t * 240 + j] = make_double2((double)cosl(ang), (double)sinl(ang));
+            }
+        FT8B_CUDA_TRY(cudaMalloc(&p.tw2, sizeof(double2) * t2.size()));
+        FT8B_CUDA_TRY(cudaMalloc(&p.tw3, sizeof(double2) * t3.size()));
+        FT8B_CUDA_TRY(cudaMemcpy(p.tw2, t2.data(), sizeof(double2) * t2.size(), cudaMemcpyHostToDevice));
+        FT8B_CUDA_TRY(cudaMemcpy(p.tw3, t3.data(), sizeof(double2) * t3.size(), cudaMemcpyHostToDevice));
+        p.fast = 1;
+    }
     auto ins = g_plans.emplace(key, p);
     *out = &ins.first->second;
     return 0;
@@ -333,6 +356,8 @@ int release_plans() {
         cudaFree(kv.second.tw);
         cudaFree(kv.second.twpost);
         cudaFree(kv.second.win);
+        cudaFree(kv.second.tw2);
+        cudaFree(kv.second.tw3);
     }
     g_plans.clear();
     return 0;
@@ -353,6 +378,19 @@ int stft_db(const void *wave, int wave_dtype, int64_t n_slots, int64_t n_samples
     const StftPlan *plan = nullptr;
     int rc = get_plan(nperseg, nfft, &plan);
     if (rc) return rc;
+    const char *force_generic = getenv("FT8B_STFT_GENERIC");
+    if (plan->fast && !(force_generic && force_generic[0] == '1')) {
+        Stft1920Args f;
+        f.wave = wave; f.n_slots = n_slots; f.slot_stride = slot_stride; f.hop = hop;
+        f.win = plan->win; f.tw2 = plan->tw2; f.tw3 = plan->tw3; f.twpost = plan->twpost; f.scale = plan->scale;
+        f.bin_lo = bin_lo; f.bin_hi = bin_hi; f.frame_lo = frame_lo; f.frames_out = frame_hi - frame_lo; f.mag = mag;
+        const int64_t items = n_slots * f.frames_out;
+        int64_t g1920 = items < 148 * 32 ? items : 148 * 32;
+        if (wave_dtype == FT8B_DTYPE_F32) stft1920_kernel<float><<<(unsigned)g1920, kStft1920Threads, 0, stream>>>(f);
+        else stft1920_kernel<double><<<(unsigned)g1920, kStft1920Threads, 0, stream>>>(f);
+        FT8B_LAUNCH_CHECK("stft1920_kernel");
+        return 0;
+    }
     StftArgs a;
     a.wave = wave; a.dtype = wave_dtype; a.n_slots = n_slots; a.slot_stride = slot_stride;
     a.nperseg = nperseg; a.hop = hop; a.nfft = nfft; a.M = plan->M; a.even = plan->even;

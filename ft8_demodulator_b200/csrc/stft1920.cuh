@@ -1,0 +1,238 @@
+// stft1920.cuh - specialised S1 kernel for the canonical FT8 geometry (fs = 12 kHz, osr 2x2):
+// nperseg = 1920, nfft = 3840, i.e. a packed real transform of M = 1920 complex float64 points.
+//
+// Plan (validated index-for-index by tools/model_stft1920.py): three in-place Stockham passes
+// 15 x 16 x 8 with 128 threads per frame.
+//   P1 radix 15, Ns = 1   : reads the windowed audio straight from global memory (the upper half of the
+//                           zero-padded frame never exists in memory), writes s[j*15 + f]
+//   P2 radix 16, Ns = 15  : s[j + 120 t] * W240^(t k)  ->  s[(j-k)*16 + k + 15 f]
+//   P3 radix  8, Ns = 240 : thread i owns butterflies i and 240-i, so Z[k] and Z[M-k] meet in registers;
+//                           the real-FFT untangling, |X|^2 scaling, +1e-12, 10*log10 and the band crop
+//                           are applied there and the dB values go straight to HBM.
+// Shared-memory traffic per frame is 4 x 30 KB (one write + read per pass boundary), 4 block barriers.
+#pragma once
+#include "common.cuh"
+
+namespace ft8b {
+
+constexpr int kM1920 = 1920;
+constexpr int kStft1920Threads = 128;
+
+struct Stft1920Args {
+    const void *wave;
+    int64_t n_slots, slot_stride;
+    int hop;
+    const double *win;        // [1920]
+    const double2 *tw2;       // [16][15]  exp(-2*pi*i*t*k/240)
+    const double2 *tw3;       // [8][240]  exp(-2*pi*i*t*j/1920)
+    const double2 *twpost;    // [1921]    exp(-2*pi*i*k/3840)
+    double scale;
+    int bin_lo, bin_hi;
+    int64_t frame_lo, frames_out;
+    double *mag;
+};
+
+namespace f1920 {
+
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ double2 mul_mi(double2 a) { return make_double2(a.y, -a.x); }   // * (-i)
+__device__ __forceinline__ double2 mul_pi(double2 a) { return make_double2(-a.y, a.x); }   // * (+i)
+// multiply by the constant (c - i*s)
+__device__ __forceinline__ double2 cmulc(double2 a, double c, double s) {
+    return make_double2(a.x * c + a.y * s, a.y * c - a.x * s);
+}
+
+__device__ __forceinline__ void bf4(double2 &a, double2 &b, double2 &c, double2 &d) {
+    const double2 s02 = cadd(a, c), d02 = csub(a, c), s13 = cadd(b, d), d13 = csub(b, d);
+    a = cadd(s02, s13);
+    b = cadd(d02, mul_mi(d13));
+    c = csub(s02, s13);
+    d = cadd(d02, mul_pi(d13));
+}
+__device__ __forceinline__ void bf3(double2 &a, double2 &b, double2 &c) {
+    const double kS = 0.86602540378443864676;
+    const double2 t1 = cadd(b, c);
+    const double2 t2 = make_double2(a.x - 0.5 * t1.x, a.y - 0.5 * t1.y);
+    const double2 d = csub(b, c);
+    const double2 t3 = make_double2(kS * d.x, kS * d.y);
+    a = cadd(a, t1);
+    b = cadd(t2, mul_mi(t3));
+    c = cadd(t2, mul_pi(t3));
+}
+__device__ __forceinline__ void bf5(double2 &u0, double2 &u1, double2 &u2, double2 &u3, double2 &u4) {
+    const double c1 = 0.30901699437494742410, c2 = -0.80901699437494742410;
+    const double s1 = 0.95105651629515357212, s2 = 0.58778525229247312917;
+    const double2 a = u0;
+    const double2 t1 = cadd(u1, u4), t2 = cadd(u2, u3), t3 = csub(u1, u4), t4 = csub(u2, u3);
+    const double2 m1 = make_double2(a.x + c1 * t1.x + c2 * t2.x, a.y + c1 * t1.y + c2 * t2.y);
+    const double2 m2 = make_double2(a.x + c2 * t1.x + c1 * t2.x, a.y + c2 * t1.y + c1 * t2.y);
+    const double2 n1 = make_double2(s1 * t3.x + s2 * t4.x, s1 * t3.y + s2 * t4.y);
+    const double2 n2 = make_double2(s2 * t3.x - s1 * t4.x, s2 * t3.y - s1 * t4.y);
+    u0 = make_double2(a.x + t1.x + t2.x, a.y + t1.y + t2.y);
+    u1 = cadd(m1, mul_mi(n1));
+    u4 = cadd(m1, mul_pi(n1));
+    u2 = cadd(m2, mul_mi(n2));
+    u3 = cadd(m2, mul_pi(n2));
+}
+
+// 15-point DFT, t = 3a + b in, f = q + 5r out (in place, natural order on both sides)
+__device__ __forceinline__ void bf15(double2 (&x)[15]) {
+    // cos/sin(2*pi*m/15)
+    const double C1 = 0.91354545764260089550, S1 = 0.40673664307580020775;
+    const double C2 = 0.66913060635885821383, S2 = 0.74314482547739423501;
+    const double C3 = 0.30901699437494742410, S3 = 0.95105651629515357212;
+    const double C4 = -0.10452846326765347140, S4 = 0.99452189536827333692;
+    const double C6 = -0.80901699437494742410, S6 = 0.58778525229247312917;
+    const double C8 = -0.97814760073380563793, S8 = -0.20791169081775933710;
+    bf5(x[0], x[3], x[6], x[9], x[12]);     // b = 0 : Y0[q] in x[3q]
+    bf5(x[1], x[4], x[7], x[10], x[13]);    // b = 1 : Y1[q] in x[3q+1]
+    bf5(x[2], x[5], x[8], x[11], x[14]);    // b = 2 : Y2[q] in x[3q+2]
+    x[4] = cmulc(x[4], C1, S1);   x[5] = cmulc(x[5], C2, S2);     // q = 1 : W15^1, W15^2
+    x[7] = cmulc(x[7], C2, S2);   x[8] = cmulc(x[8], C4, S4);     // q = 2 : W15^2, W15^4
+    x[10] = cmulc(x[10], C3, S3); x[11] = cmulc(x[11], C6, S6);   // q = 3 : W15^3, W15^6
+    x[13] = cmulc(x[13], C4, S4); x[14] = cmulc(x[14], C8, S8);   // q = 4 : W15^4, W15^8
+    bf3(x[0], x[1], x[2]);        // q = 0 : f = 0, 5, 10
+    bf3(x[3], x[4], x[5]);        // q = 1 : f = 1, 6, 11
+    bf3(x[6], x[7], x[8]);
+    bf3(x[9], x[10], x[11]);
+    bf3(x[12], x[13], x[14]);
+    // now x[3q + r] = X[q + 5r]; caller maps with out_index15()
+}
+__device__ __forceinline__ constexpr int out15(int pos) { return (pos / 3) + 5 * (pos % 3); }   // f held at x[pos]
+
+// 16-point DFT, t = 4a + b in, f = q + 4r out; after the call x[4q + r] = X[q + 4r]
+__device__ __forceinline__ void bf16(double2 (&x)[16]) {
+    const double C = 0.92387953251128675613, S = 0.38268343236508977173, H = 0.70710678118654752440;
+    bf4(x[0], x[4], x[8], x[12]);     // b = 0 : Y0[q] in x[4q]
+    bf4(x[1], x[5], x[9], x[13]);     // b = 1 : Y1[q] in x[4q+1]
+    bf4(x[2], x[6], x[10], x[14]);
+    bf4(x[3], x[7], x[11], x[15]);
+    // Yb[q] *= W16^(b q)
+    x[5] = cmulc(x[5], C, S);    x[6] = cmulc(x[6], H, H);    x[7] = cmulc(x[7], S, C);        // q=1: W^1 W^2 W^3
+    x[9] = cmulc(x[9], H, H);    x[10] = mul_mi(x[10]);       x[11] = cmulc(x[11], -H, H);     // q=2: W^2 W^4 W^6
+    x[13] = cmulc(x[13], S, C);  x[14] = cmulc(x[14], -H, H); x[15] = cmulc(x[15], -C, -S);    // q=3: W^3 W^6 W^9
+    bf4(x[0], x[1], x[2], x[3]);
+    bf4(x[4], x[5], x[6], x[7]);
+    bf4(x[8], x[9], x[10], x[11]);
+    bf4(x[12], x[13], x[14], x[15]);
+}
+__device__ __forceinline__ constexpr int out16(int pos) { return (pos / 4) + 4 * (pos % 4); }
+
+// 8-point DFT in place, natural order in and out
+__device__ __forceinline__ void bf8(double2 (&a)[8]) {
+    const double H = 0.70710678118654752440;
+    double2 b0 = cadd(a[0], a[4]), b1 = cadd(a[1], a[5]), b2 = cadd(a[2], a[6]), b3 = cadd(a[3], a[7]);
+    double2 c0 = csub(a[0], a[4]), c1 = csub(a[1], a[5]), c2 = csub(a[2], a[6]), c3 = csub(a[3], a[7]);
+    c1 = cmulc(c1, H, H);
+    c2 = mul_mi(c2);
+    c3 = cmulc(c3, -H, H);
+    bf4(b0, b1, b2, b3);
+    bf4(c0, c1, c2, c3);
+    a[0] = b0; a[1] = c0; a[2] = b1; a[3] = c1; a[4] = b2; a[5] = c2; a[6] = b3; a[7] = c3;
+}
+
+__device__ __forceinline__ double to_db(double re, double im, double scale) {
+    return 10.0 * log10(1e-12 + (re * re + im * im) * scale);
+}
+
+// Untangle the pair (Z[k], Z[M-k]) of the packed transform and emit dB for bins k and M-k.
+__device__ __forceinline__ void emit_pair(double2 z, double2 zr, int k, const Stft1920Args &a, double *out) {
+    const double2 zc = make_double2(zr.x, -zr.y);
+    const double2 e = make_double2(0.5 * (z.x + zc.x), 0.5 * (z.y + zc.y));
+    const double2 p = cmul(__ldg(&a.twpost[k]), csub(z, zc));
+    const int k2 = kM1920 - k;
+    if (k >= a.bin_lo && k < a.bin_hi) out[k - a.bin_lo] = to_db(e.x + 0.5 * p.y, e.y - 0.5 * p.x, a.scale);
+    if (k2 != k && k2 >= a.bin_lo && k2 < a.bin_hi) out[k2 - a.bin_lo] = to_db(e.x - 0.5 * p.y, e.y + 0.5 * p.x, a.scale);
+}
+
+}  // namespace f1920
+
+template <typename WaveT>
+__global__ void __launch_bounds__(kStft1920Threads, 4) stft1920_kernel(const Stft1920Args a) {
+    using namespace f1920;
+    __shared__ double2 s[kM1920];
+    const int tid = threadIdx.x;
+    const int64_t n_items = a.n_slots * a.frames_out;
+    const int Fout = a.bin_hi - a.bin_lo;
+    for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int64_t slot = item / a.frames_out;
+        const int64_t fr = item - slot * a.frames_out;
+        const WaveT *x = reinterpret_cast<const WaveT *>(a.wave) + slot * a.slot_stride + (fr + a.frame_lo) * a.hop;
+        double *out = a.mag + (slot * a.frames_out + fr) * (int64_t)Fout;
+        // ---------------- P1: radix 15, inputs z[j + 128 t] = (w x)[2n] + i (w x)[2n+1], zero for n >= 960
+        {
+            double2 u[15];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const int n = tid + 128 * t;
+                if (t < 7 || tid < 64) {
+                    const double w0 = __ldg(&a.win[2 * n]), w1 = __ldg(&a.win[2 * n + 1]);
+                    u[t] = make_double2(w0 * (double)x[2 * n], w1 * (double)x[2 * n + 1]);
+                } else {
+                    u[t] = make_double2(0.0, 0.0);
+                }
+            }
+#pragma unroll
+            for (int t = 8; t < 15; ++t) u[t] = make_double2(0.0, 0.0);
+            bf15(u);
+#pragma unroll
+            for (int pos = 0; pos < 15; ++pos) s[tid * 15 + out15(pos)] = u[pos];
+        }
+        __syncthreads();
+        // ---------------- P2: radix 16, Ns = 15
+        {
+            double2 u[16];
+            const int j = tid, k = tid % 15;
+            if (tid < 120) {
+#pragma unroll
+                for (int t = 0; t < 16; ++t) u[t] = s[j + 120 * t];
+#pragma unroll
+                for (int t = 1; t < 16; ++t) u[t] = cmul(u[t], __ldg(&a.tw2[t * 15 + k]));
+                bf16(u);
+            }
+            __syncthreads();
+            if (tid < 120) {
+                const int j0 = (j - k) * 16 + k;
+#pragma unroll
+                for (int pos = 0; pos < 16; ++pos) s[j0 + 15 * out16(pos)] = u[pos];
+            }
+        }
+        __syncthreads();
+        // ---------------- P3: radix 8, Ns = 240, paired butterflies + untangling + dB store
+        if (tid >= 1 && tid < 120) {
+            double2 u1[8], u2[8];
+            const int j1 = tid, j2 = 240 - tid;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) { u1[t] = s[j1 + 240 * t]; u2[t] = s[j2 + 240 * t]; }
+#pragma unroll
+            for (int t = 1; t < 8; ++t) {
+                u1[t] = cmul(u1[t], __ldg(&a.tw3[t * 240 + j1]));
+                u2[t] = cmul(u2[t], __ldg(&a.tw3[t * 240 + j2]));
+            }
+            bf8(u1);
+            bf8(u2);
+#pragma unroll
+            for (int t = 0; t < 8; ++t) emit_pair(u1[t], u2[7 - t], j1 + 240 * t, a, out);
+        } else if (tid == 0) {
+            double2 u0[8], um[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) { u0[t] = s[240 * t]; um[t] = s[120 + 240 * t]; }
+#pragma unroll
+            for (int t = 1; t < 8; ++t) um[t] = cmul(um[t], __ldg(&a.tw3[t * 240 + 120]));
+            bf8(u0);
+            bf8(um);
+            emit_pair(u0[0], u0[0], 0, a, out);                                  // bins 0 and 1920
+#pragma unroll
+            for (int t = 1; t <= 4; ++t) emit_pair(u0[t], u0[8 - t], 240 * t, a, out);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) emit_pair(um[t], um[7 - t], 120 + 240 * t, a, out);
+        }
+        __syncthreads();   // s is rewritten by the next frame's P1
+    }
+}
+
+}  // namespace ft8b

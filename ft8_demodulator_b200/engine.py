@@ -198,10 +198,28 @@ def make_params(sample_rate, bins_per_tone, steps_per_symbol, max_candidates, mi
                              int(frame_hi), int(chunk_slots), 0)
 
 
-class SlotDecoder:
-    """Reusable batched decoder: owns the result tensors and the chunk workspace for one geometry."""
+def alloc_slot_decodes(B: int, K: int, dev) -> SlotDecodes:
+    return SlotDecodes(
+        cand_time=torch.zeros((B, K), dtype=torch.int32, device=dev),
+        cand_freq=torch.zeros((B, K), dtype=torch.int32, device=dev),
+        cand_score=torch.zeros((B, K), dtype=_F64, device=dev), n_cand=torch.zeros((B,), dtype=torch.int32, device=dev),
+        ok=torch.zeros((B, K), dtype=torch.uint8, device=dev),
+        ldpc_errors=torch.zeros((B, K), dtype=torch.int32, device=dev),
+        crc_extracted=torch.zeros((B, K), dtype=torch.int32, device=dev),
+        crc_calculated=torch.zeros((B, K), dtype=torch.int32, device=dev),
+        payload=torch.zeros((B, K, 10), dtype=torch.uint8, device=dev))
 
-    def __init__(self, n_slots: int, n_samples: int, params: _lib.DecodeParams, device=None):
+
+def slice_slot_decodes(o: SlotDecodes, lo: int, hi: int) -> SlotDecodes:
+    """Row range [lo, hi) of every array (views: rows are contiguous)."""
+    return SlotDecodes(*[getattr(o, f)[lo:hi] for f in o.__dataclass_fields__])
+
+
+class SlotDecoder:
+    """Reusable batched decoder: owns the chunk workspace (and, unless told otherwise, the result
+    tensors) for one geometry."""
+
+    def __init__(self, n_slots: int, n_samples: int, params: _lib.DecodeParams, device=None, alloc_out: bool = True):
         self.device = device or require_cuda()
         self.n_slots, self.n_samples, self.params = int(n_slots), int(n_samples), params
         K = params.max_candidates
@@ -211,25 +229,52 @@ class SlotDecoder:
         if nbytes < 0:
             _lib.check(int(nbytes), "ft8b_decode_workspace_bytes")
         self.workspace = torch.empty((max(int(nbytes), 16),), dtype=torch.uint8, device=self.device)
-        B, dev = self.n_slots, self.device
-        self.out = SlotDecodes(
-            cand_time=torch.zeros((B, K), dtype=torch.int32, device=dev),
-            cand_freq=torch.zeros((B, K), dtype=torch.int32, device=dev),
-            cand_score=torch.zeros((B, K), dtype=_F64, device=dev), n_cand=torch.zeros((B,), dtype=torch.int32, device=dev),
-            ok=torch.zeros((B, K), dtype=torch.uint8, device=dev),
-            ldpc_errors=torch.zeros((B, K), dtype=torch.int32, device=dev),
-            crc_extracted=torch.zeros((B, K), dtype=torch.int32, device=dev),
-            crc_calculated=torch.zeros((B, K), dtype=torch.int32, device=dev),
-            payload=torch.zeros((B, K, 10), dtype=torch.uint8, device=dev))
+        self.out = alloc_slot_decodes(self.n_slots, K, self.device) if alloc_out else None
 
-    def run(self, wave: torch.Tensor) -> SlotDecodes:
+    def run(self, wave: torch.Tensor, out: SlotDecodes = None) -> SlotDecodes:
         """wave [B, N] f32/f64 on the device.  Asynchronous on the current stream."""
         assert wave.is_cuda and wave.dim() == 2 and wave.stride(1) == 1
         assert wave.shape[0] == self.n_slots and wave.shape[1] == self.n_samples
-        o = self.out
+        o = out if out is not None else self.out
         _lib.check(_lib.lib().ft8b_decode_slots(
             _p(wave), wave_dtype_code(wave), self.n_slots, self.n_samples, wave.stride(0), C.byref(self.params),
             _p(self.workspace), self.workspace.numel(), _p(o.cand_time), _p(o.cand_freq), _p(o.cand_score), _p(o.n_cand),
             _p(o.ok), _p(o.ldpc_errors), _p(o.crc_extracted), _p(o.crc_calculated), _p(o.payload), _stream()),
             "ft8b_decode_slots")
         return o
+
+
+def decode_host_batch(waves: torch.Tensor, params: _lib.DecodeParams, piece_slots: int = 512, device=None) -> SlotDecodes:
+    """Host [B, N] tensor -> device results, with the H2D copy of piece i+1 overlapping the kernels of
+    piece i (two device staging buffers, one copy stream).  Pinned host memory copies asynchronously."""
+    dev = device or require_cuda()
+    B, N = waves.shape
+    K = params.max_candidates
+    out = alloc_slot_decodes(B, K, dev)
+    if B == 0:
+        return out
+    piece = min(piece_slots, B)
+    bufs = [torch.empty((piece, N), dtype=waves.dtype, device=dev) for _ in range(2 if B > piece else 1)]
+    decoders = {}
+    copy_stream = torch.cuda.Stream(device=dev)
+    main = torch.cuda.current_stream(dev)
+    done = [None, None]
+    copy_stream.wait_stream(main)
+    for i, lo in enumerate(range(0, B, piece)):
+        hi = min(lo + piece, B)
+        n = hi - lo
+        buf = bufs[i % len(bufs)]
+        with torch.cuda.stream(copy_stream):
+            if done[i % len(bufs)] is not None:
+                copy_stream.wait_event(done[i % len(bufs)])
+            buf[:n].copy_(waves[lo:hi], non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(copy_stream)
+        main.wait_event(ready)
+        if n not in decoders:
+            decoders[n] = SlotDecoder(n, N, params, device=dev, alloc_out=False)
+        decoders[n].run(buf[:n], out=slice_slot_decodes(out, lo, hi))
+        ev = torch.cuda.Event()
+        ev.record(main)
+        done[i % len(bufs)] = ev
+    return out

@@ -241,7 +241,7 @@ class BatchDecodes:
 
 def decode_slots(waves, sample_rate, bins_per_tone: int = 2, steps_per_symbol: int = 2, max_candidates: int = 20,
                  min_score=10, max_iterations: int = 20, freq_min=None, freq_max=None, time_min=None, time_max=None,
-                 chunk_slots: int = 0, return_device: bool = False):
+                 chunk_slots: int = 0, return_device: bool = False, piece_slots: int = 512):
     """Decode a batch of equal-length slots: waves [B, N] (NumPy or torch, host or device, float32/float64).
 
     Per-slot semantics are exactly decode_ft8_message's.  Host input is copied to the GPU inside this
@@ -262,13 +262,14 @@ def decode_slots(waves, sample_rate, bins_per_tone: int = 2, steps_per_symbol: i
     g = decode_geometry(N, sample_rate, bins_per_tone, steps_per_symbol, freq_min, freq_max, time_min, time_max)
     params = engine.make_params(sample_rate, bins_per_tone, steps_per_symbol, max_candidates, min_score, max_iterations,
                                 g["bin_lo"], g["bin_hi"], g["frame_lo"], g["frame_hi"], chunk_slots)
-    dec = engine.SlotDecoder(B, N, params, device=dev)
-    if B and g["T_all"] > 0:
-        wdev = waves if waves.is_cuda else waves.to(dev, non_blocking=True)
-        if wdev.stride(1) != 1:
-            wdev = wdev.contiguous()
-        dec.run(wdev)
-    out = dec.out
+    if max_candidates > _lib.MAX_CANDIDATES:
+        raise NotImplementedError("max_candidates=%d exceeds the kernel limit %d" % (max_candidates, _lib.MAX_CANDIDATES))
+    if B == 0 or g["T_all"] <= 0:
+        out = engine.alloc_slot_decodes(B, int(max_candidates), dev)
+    elif waves.is_cuda:
+        out = engine.SlotDecoder(B, N, params, device=dev).run(waves if waves.stride(1) == 1 else waves.contiguous())
+    else:
+        out = engine.decode_host_batch(waves.contiguous(), params, piece_slots=piece_slots, device=dev)
     if return_device:
         return out
     return BatchDecodes(out.cpu(), sample_rate, bins_per_tone)

@@ -43,6 +43,21 @@ def crc14(message: bytes, num_bits: int) -> int:
     return rem
 
 
+def crc14_bits(payload_bits: np.ndarray) -> np.ndarray:
+    """Vectorised CRC-14 of [n,77] payload bit arrays (zero-extended to 82 bits) -> [n,14] CRC bits, MSB first."""
+    n = payload_bits.shape[0]
+    bits = np.zeros((n, 88), dtype=np.int64)
+    bits[:, :77] = payload_bits
+    by = np.packbits(bits.astype(np.uint8), axis=1).astype(np.int64)      # [n,11] message bytes
+    rem = np.zeros(n, dtype=np.int64)
+    for bit in range(82):
+        if bit % 8 == 0:
+            rem ^= by[:, bit // 8] << 6
+        top = (rem & 0x2000) != 0
+        rem = np.where(top, (rem << 1) ^ 0x2757, rem << 1) & 0x3FFF
+    return ((rem[:, None] >> np.arange(13, -1, -1)[None, :]) & 1).astype(np.uint8)
+
+
 def add_crc(payload10) -> np.ndarray:
     """77-bit payload (10 bytes, low 3 bits of byte 9 ignored) -> a91 (12 bytes). crc.py:25-47."""
     a91 = np.zeros(12, dtype=np.uint8)
@@ -200,7 +215,9 @@ def c5_llr(n_words: int, seed: int = 0, snr2500_range=(-26.0, -20.0)):
     ft8_decode.py:151-198, vectorised).  Returns (llr[n,174] float64, codeword bits[n,174] uint8)."""
     rng = np.random.default_rng(seed)
     G = _generator_rows().astype(np.uint8)
-    msg = rng.integers(0, 2, (n_words, _C.FTX_LDPC_K), dtype=np.uint8)
+    msg = np.zeros((n_words, _C.FTX_LDPC_K), dtype=np.uint8)
+    msg[:, :77] = rng.integers(0, 2, (n_words, 77), dtype=np.uint8)
+    msg[:, 77:] = crc14_bits(msg[:, :77])
     par = (msg.astype(np.int32) @ G.T.astype(np.int32)) & 1
     bits = np.concatenate([msg, par.astype(np.uint8)], axis=1)
     sym = bits.reshape(n_words, 58, 3)

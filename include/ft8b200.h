@@ -155,6 +155,11 @@ int ft8b_decode_slots(const void *wave, int wave_dtype, int64_t n_slots, int64_t
 
 /* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
 int64_t ft8b_launch_count(void);
+/* Per-stage device timing of ft8b_decode_slots (cudaEvent pairs on the launching stream).
+ * ft8b_stage_timing(1) resets and enables, (0) disables.  ft8b_stage_times fills ms[5] / launches[5]
+ * for the stages {stft, sync, select, llr, ldpc} accumulated since the reset (synchronises). */
+int ft8b_stage_timing(int enable);
+int ft8b_stage_times(double *ms, int64_t *launches);
 
 #ifdef __cplusplus
 }

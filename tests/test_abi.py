@@ -1,0 +1,86 @@
+"""The C-ABI library loads and exports every symbol include/ft8b200.h declares; host-only entry
+points agree with the oracle; compute entry points fail loudly without a GPU (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+from ft8_demodulator_b200 import _lib
+
+
+def declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "ft8b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(ft8b_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = C.CDLL(_lib.LIB_PATH)
+    names = declared_symbols()
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(L, n), "libft8b200.so does not export " + n
+    # and the ctypes binding covers exactly the declared set
+    assert sorted(_lib.SIGNATURES) == names
+
+
+def test_version_and_error_slot():
+    L = _lib.lib()
+    assert L.ft8b_version() == 100
+    a, b, c = C.c_int(), C.c_int(), C.c_int()
+    assert L.ft8b_plan(-1.0, 2, 2, C.byref(a), C.byref(b), C.byref(c)) == _lib.ERR_ARG
+    assert "ft8b_plan" in _lib.last_error()
+    with pytest.raises(ValueError):
+        _lib.plan(12000, 0, 2)
+
+
+@pytest.mark.parametrize("fs", [12000, 6000, 10e3, 3500, 20000, 2000, 32768, 4500, 9999.5, 1_000_000])
+@pytest.mark.parametrize("b,s", [(2, 2), (4, 4), (10, 10), (1, 1), (2, 8), (3, 5000)])
+def test_geometry_matches_oracle(orc, fs, b, s):
+    assert _lib.plan(fs, b, s) == orc.plan(fs, b, s)
+    nperseg, hop, nfft = _lib.plan(fs, b, s)
+    for n in (0, 10, nperseg - 1, nperseg, nperseg + hop, 180000):
+        assert _lib.num_frames(n, nperseg, hop) == orc.lib().orc_num_frames(n, nperseg, hop)
+
+
+@pytest.mark.parametrize("F,T,s,b", [(1920, 186, 2, 2), (100, 50, 2, 2), (64, 400, 4, 1), (14, 300, 1, 2), (961, 186, 2, 2)])
+def test_search_ranges_match_oracle(orc, F, T, s, b):
+    t0, nt, nf = _lib.search_ranges(T, F, s, b)
+    o = orc.search_ranges(F, T, s, b)
+    assert (t0, t0 + nt, 0, nf) == o
+
+
+def test_workspace_query_is_host_only():
+    from ft8_demodulator_b200 import engine
+    p = engine.make_params(12000, 2, 2, 20, 1, 20, 0, 1920, 0, 186, 16)
+    n = _lib.lib().ft8b_decode_workspace_bytes(C.byref(p), 64, 180000)
+    assert n >= 16 * 8 * (186 * 1920 + 88 * 1906) + 64 * 20 * 174 * 8
+    bad = engine.make_params(12000, 2, 2, 20, 1, 20, 0, 5000, 0, 186, 16)
+    assert _lib.lib().ft8b_decode_workspace_bytes(C.byref(bad), 64, 180000) < 0
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback():
+    from ft8_demodulator_b200.ft8_demodulator import ft8_decode as fd, ldpc_decoder as ld, spectrogram_analyse as sa
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        fd.decode_ft8_message(np.zeros(180000), 12000)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ld.bp_decode(np.ones(174), 5)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        sa.calculate_spectrogram(np.zeros(180000), 12000)
+    # and the raw ABI reports a CUDA/no-device error instead of computing anything
+    rc = _lib.lib().ft8b_ldpc_check(1, 1, 1, None)
+    assert rc != 0
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "ft8_demodulator_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "ft8_oracle" not in src and "reference_loader" not in src, f

@@ -1,0 +1,374 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Everything goes through the C ABI
+(ctypes) and is compared with the CPU oracle on the same seeded inputs and with the committed
+golden fixtures generated from the unmodified reference.
+
+Tolerances (all arithmetic is float64 on both sides):
+  spectrogram  |dB difference| <= 1e-9   (different FFT factorisation; north_star allows 1e-4 relative)
+  sync scores  |difference|    <= 1e-9   (same spectrogram in: <= 1e-12, summation order differs)
+  LLRs, BP hard decisions, ldpc_errors, CRC fields, payloads, candidate indices: exact
+"""
+import json
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_case, load_golden
+from ft8_demodulator_b200 import engine, synth
+from ft8_demodulator_b200.ft8_demodulator import ft8_decode as fd
+from ft8_demodulator_b200.ft8_demodulator import ldpc_decoder as ld
+from ft8_demodulator_b200.ft8_demodulator import spectrogram_analyse as sa
+
+pytestmark = pytest.mark.gpu
+
+SPEC_TOL_DB = 1e-9
+SCORE_TOL = 1e-9
+
+
+def dev():
+    return engine.require_cuda()
+
+
+def gpu_mag(wave, fs, b, s, dtype=np.float64):
+    nperseg, hop, nfft = fd._lib.plan(fs, b, s)
+    T = fd._lib.num_frames(len(wave), nperseg, hop)
+    w = engine._dev(np.asarray(wave, dtype=dtype).reshape(1, -1))
+    return engine.stft_db(w, nperseg, hop, nfft, 0, (nfft + 1) // 2, 0, T)   # [1,T,F]
+
+
+# ------------------------------------------------------------------------------------------ S1
+@pytest.mark.parametrize("fs,b,s,n", [(12000, 2, 2, 180000), (6000, 2, 2, 90000), (10e3, 4, 4, 60000), (3500, 2, 2, 52500),
+                                      (20000, 2, 2, 100000), (2000, 2, 2, 30000), (32768, 2, 2, 80000),
+                                      (12000, 1, 1, 40000), (12000, 3, 5, 40000), (4500, 2, 3, 30000)])
+def test_stft_vs_oracle(orc, fs, b, s, n):
+    rng = np.random.default_rng(int(fs) + b + s)
+    x = rng.standard_normal(n) * 0.3 + np.sin(2 * np.pi * 440.0 * np.arange(n) / fs)
+    x = x.astype(np.float32).astype(np.float64)
+    ref = orc.spectrogram_pos(x, fs, b, s)                       # [F,T]
+    for dt in (np.float64, np.float32):
+        got = gpu_mag(x, fs, b, s, dt)[0].cpu().numpy().T
+        assert got.shape == ref.shape
+        assert np.abs(got - ref).max() < SPEC_TOL_DB
+
+
+def test_stft_crop_and_batch(orc):
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((3, 50000)).astype(np.float32)
+    nperseg, hop, nfft = 1920, 960, 3840
+    w = engine._dev(x)
+    full = engine.stft_db(w, nperseg, hop, nfft, 0, 1921, 0, 51)
+    crop = engine.stft_db(w, nperseg, hop, nfft, 100, 400, 7, 33)
+    assert torch.equal(crop, full[:, 7:33, 100:400].contiguous())
+    for i in range(3):
+        ref = orc.spectrogram_pos(x[i].astype(np.float64), 12000, 2, 2)
+        assert np.abs(full[i, :, :1920].cpu().numpy().T - ref).max() < SPEC_TOL_DB
+    # Nyquist bin (row -fs/2 of the reference's two-sided layout) against a direct NumPy transform
+    win = 0.5 - 0.5 * np.cos(2 * np.pi * np.arange(1920) / 1920)
+    fr = np.stack([x[0, j * 960:j * 960 + 1920].astype(np.float64) * win for j in range(51)])
+    nyq = 10 * np.log10(1e-12 + np.abs(np.fft.rfft(fr, n=3840)[:, 1920]) ** 2 / win.sum() ** 2)
+    assert np.abs(full[0, :, 1920].cpu().numpy() - nyq).max() < 1e-8
+
+
+def test_stft_fast_path_equals_generic_path(monkeypatch):
+    """The specialised 15x16x8 kernel (nperseg 1920 / nfft 3840) against the generic mixed-radix kernel."""
+    rng = np.random.default_rng(11)
+    x = engine._dev((rng.standard_normal((2, 30000)) * 1e-3).astype(np.float64))
+    fast = engine.stft_db(x, 1920, 960, 3840, 0, 1921, 0, 30)
+    monkeypatch.setenv("FT8B_STFT_GENERIC", "1")
+    generic = engine.stft_db(x, 1920, 960, 3840, 0, 1921, 0, 30)
+    monkeypatch.delenv("FT8B_STFT_GENERIC")
+    assert (fast - generic).abs().max().item() < 1e-9
+    f32 = engine.stft_db(x.to(torch.float32), 1920, 960, 3840, 5, 900, 3, 17)
+    ref = engine.stft_db(x.to(torch.float32).to(torch.float64), 1920, 960, 3840, 5, 900, 3, 17)
+    assert torch.equal(f32, ref)
+
+
+def test_stft_signal_floor():
+    """All-zero audio hits the 1e-12 floor exactly: 10*log10(1e-12) (spectrogram_analyse.py:60)."""
+    got = gpu_mag(np.zeros(20000), 12000, 2, 2)
+    assert torch.all(got == 10.0 * np.log10(1e-12))
+
+
+def test_calculate_spectrogram_dropin(c1_slot):
+    g = load_golden("c1.npz")
+    S, f, t = sa.calculate_spectrogram(c1_slot, 12000, 2, 2)
+    assert S.shape == (3840, 186) and S.dtype == np.float64
+    np.testing.assert_array_equal(f, g["spec_f"])
+    np.testing.assert_allclose(t, g["spec_t"], rtol=0, atol=0)
+    pos = S[f >= 0]
+    assert np.abs(pos[150:214] - g["spec_rows_150_214"]).max() < SPEC_TOL_DB
+    assert np.abs(pos[::97] - g["spec_rows_stride"]).max() < SPEC_TOL_DB
+    # two-sided symmetry for real input: row of -f equals row of +f
+    assert np.array_equal(S[1920 - 5], S[1920 + 5]) and np.array_equal(S[1], S[3839])
+    S32, _, _ = sa.calculate_spectrogram(c1_slot.astype(np.float32), 12000, 2, 2)
+    assert S32.dtype == np.float32 and np.abs(S32 - S).max() < 1e-4
+    e = sa.calculate_spectrogram(np.zeros(10), 12000)
+    assert e[0].shape == (1, 0) and len(e[1]) == 0 and len(e[2]) == 0
+    sub, fsub = sa.select_frequency_band(S, f, 0, 3000)
+    assert sub.shape[0] == 961 and fsub[0] == 0 and fsub[-1] == 3000
+
+
+# ------------------------------------------------------------------------------------------ S2
+@pytest.mark.parametrize("F,T,s,b", [(1920, 186, 2, 2), (400, 186, 1, 2), (300, 190, 3, 1), (101, 200, 2, 2),
+                                     (500, 401, 4, 3), (64, 120, 2, 4), (257, 347, 4, 4)])
+def test_score_map_vs_oracle(orc, F, T, s, b):
+    rng = np.random.default_rng(F * 7 + T)
+    mag = (rng.standard_normal((F, T)) * 6 - 60).astype(np.float64)
+    ref = orc.score_map(mag, s, b)
+    m = engine._dev(np.ascontiguousarray(mag.T).reshape(1, T, F))
+    got, t0 = engine.sync_scores(m, s, b)
+    assert got.shape[1:] == ref.shape and t0 == -10 * s
+    if ref.size:
+        g = got[0].cpu().numpy()
+        assert np.array_equal(np.isneginf(g), np.isneginf(ref))
+        fin = np.isfinite(ref)
+        assert np.abs(g[fin] - ref[fin]).max() < 1e-12
+
+
+@pytest.mark.parametrize("K,thr", [(20, 1.0), (20, 3.0), (20, 10.0), (1, 1.0), (7, 2.0), (300, 2.5), (4096, 1.0), (50, -100.0),
+                                   (20, 100.0)])
+def test_selection_vs_oracle_on_oracle_spectrogram(orc, c1_slot, K, thr):
+    """Same float64 spectrogram on both sides -> identical candidate lists (order and indices)."""
+    mag = orc.spectrogram_pos(c1_slot, 12000, 2, 2)
+    ct, cf, cs, npass = orc.ft8_find_candidates(mag, 2, 2, K, thr)
+    m = engine._dev(np.ascontiguousarray(mag.T).reshape(1, 186, 1920))
+    scores, t0 = engine.sync_scores(m, 2, 2)
+    gt, gf, gs, gn, gp = engine.select_candidates(scores, t0, K, thr)
+    n = int(gn.cpu()[0])
+    assert n == len(ct) and int(gp.cpu()[0]) == npass
+    assert gt[0, :n].cpu().numpy().tolist() == ct.tolist()
+    assert gf[0, :n].cpu().numpy().tolist() == cf.tolist()
+    np.testing.assert_allclose(gs[0, :n].cpu().numpy(), cs, rtol=0, atol=1e-12)
+
+
+def test_selection_synthetic_maps():
+    """Selection semantics on hand-made score maps (first-K + record replacement, K > passers, none)."""
+    nt, nf = 6, 50
+    rng = np.random.default_rng(0)
+    base = rng.permutation(nt * nf).astype(np.float64).reshape(1, nt, nf) / 10.0   # distinct scores 0..29.9
+    sc = engine._dev(base)
+    flat = base.reshape(-1)
+    for K, thr in [(5, 3.0), (5, 29.95), (400, 10.0), (3, 0.0), (300, -1.0)]:
+        passers = [i for i in range(flat.size) if flat[i] >= thr]
+        H = passers[:K]
+        if len(passers) > K and H:
+            best = max(H, key=lambda i: flat[i])
+            for i in passers[K:]:
+                if flat[i] > flat[best]:
+                    H[H.index(best)] = i
+                    best = i
+        H.sort(key=lambda i: -flat[i])
+        gt, gf, gs, gn, gp = engine.select_candidates(sc, -20, K, thr)
+        n = int(gn.cpu()[0])
+        assert n == len(H) and int(gp.cpu()[0]) == len(passers)
+        assert (gt[0, :n].cpu().numpy() + 20).tolist() == [i // nf for i in H]
+        assert gf[0, :n].cpu().numpy().tolist() == [i % nf for i in H]
+
+
+# ------------------------------------------------------------------------------------------ S3
+def test_bp_golden_bit_exact():
+    g = load_golden("bp.npz")
+    for it in np.unique(g["max_iterations"]):
+        sel = g["max_iterations"] == it
+        plain, err = ld.bp_decode_batch(g["llr"][sel], int(it))
+        assert np.array_equal(err, g["min_errors"][sel])
+        assert np.array_equal(plain, g["plain"][sel])
+    p, e = ld.bp_decode(g["llr"][0], 20)
+    assert np.array_equal(p, g["plain"][0]) and e == g["min_errors"][0] and p.dtype == np.uint8
+
+
+def test_bp_vs_oracle_c5(orc):
+    """Config C5 sample: 20k low-SNR words, hard bits / min_errors / CRC flags bit-exact vs the oracle."""
+    llr, bits = synth.c5_llr(20000, seed=5)
+    out = engine.ldpc_crc(engine._dev(llr), 20)
+    plain, err = orc.bp_batch(llr, 20, n_threads=8)
+    assert np.array_equal(out.ldpc_errors.cpu().numpy(), err)
+    assert np.array_equal(out.plain.cpu().numpy(), plain)
+    ok = out.ok.cpu().numpy().astype(bool)
+    conv = err == 0
+    assert ok.sum() > 100 and np.array_equal(ok, conv & ok)
+    # converged + CRC ok words decode to the transmitted codeword's first 77 bits
+    pl = out.payload.cpu().numpy()
+    tx = np.packbits(bits[:, :80], axis=1)
+    tx[:, 9] &= 0xF8
+    assert np.array_equal(pl[ok], tx[ok][:, :10])
+    assert np.array_equal(out.crc_extracted.cpu().numpy()[ok], out.crc_calculated.cpu().numpy()[ok])
+
+
+def test_ldpc_check_and_normalize(orc):
+    rng = np.random.default_rng(9)
+    bits = rng.integers(0, 2, (64, 174), dtype=np.uint8)
+    bits[0] = 0
+    bits[1] = synth.codeword_bits(synth.C1_PAYLOAD)
+    err = engine.ldpc_check(engine._dev(bits)).cpu().numpy()
+    assert err.tolist() == [orc.ldpc_check(b) for b in bits] and err[0] == 0 and err[1] == 0
+    assert ld.ldpc_check(bits[5]) == orc.ldpc_check(bits[5])
+    v = rng.standard_normal((50, 174)) * 10 ** rng.uniform(-3, 3, (50, 1))
+    got = engine.normalize_llr_(engine._dev(v.copy())).cpu().numpy()
+    for i in range(50):
+        assert np.array_equal(got[i], orc.ftx_normalize_logl(v[i]))          # bit-exact incl. numpy's pairwise mean
+    a = v[0].copy()
+    fd.ftx_normalize_logl(a)
+    assert np.array_equal(a, got[0])
+
+
+def test_llr_and_candidate_decode_on_oracle_spectrogram(orc, c1_slot):
+    """Identical spectrogram in -> LLRs and every decode field bit-identical to the oracle."""
+    mag = orc.spectrogram_pos(c1_slot, 12000, 2, 2)
+    ct, cf, cs, _ = orc.ft8_find_candidates(mag, 2, 2, 20, 1)
+    ct = np.concatenate([ct, [-20, 67, 67, -1]]).astype(np.int32)      # edges of the time range too
+    cf = np.concatenate([cf, [0, 1905, 0, 700]]).astype(np.int32)
+    m = engine._dev(np.ascontiguousarray(mag.T).reshape(1, 186, 1920))
+    tct, tcf = engine._dev(ct.reshape(1, -1)), engine._dev(cf.reshape(1, -1))
+    nc = engine._dev(np.array([len(ct)], dtype=np.int32))
+    d = engine.decode_candidates(m, 2, 2, tct, tcf, nc, 20, want_llr=True, want_plain=True)
+    raw = engine.extract_llr(m, 2, 2, tct, tcf, nc, normalize=False)[0].cpu().numpy()
+    for i, (t, f) in enumerate(zip(ct.tolist(), cf.tolist())):
+        r = orc.ft8_decode_candidate(mag, 2, 2, t, f, 20)
+        assert np.array_equal(raw[i], orc.ft8_extract_likelihood(mag, 2, 2, t, f))
+        assert np.array_equal(d.llr[0, i].cpu().numpy(), r["llr"])
+        assert np.array_equal(d.plain[0, i].cpu().numpy(), r["plain"])
+        assert int(d.ldpc_errors[0, i]) == r["ldpc_errors"] and bool(d.ok[0, i]) == r["ok"]
+        assert int(d.crc_extracted[0, i]) == r["crc_extracted"] and int(d.crc_calculated[0, i]) == r["crc_calculated"]
+        assert bytes(d.payload[0, i].cpu().numpy()) == r["payload"]
+
+
+# ------------------------------------------------------------------------------------------ whole path
+def check_against_gold(res_arrays, gold, slot=0):
+    n = int(res_arrays.n_cand[slot])
+    assert res_arrays.cand_time[slot, :n].tolist() == gold["cand_time"].tolist()
+    assert res_arrays.cand_freq[slot, :n].tolist() == gold["cand_freq"].tolist()
+    np.testing.assert_allclose(res_arrays.cand_score[slot, :n].numpy(), gold["cand_score"], rtol=0, atol=SCORE_TOL)
+    assert res_arrays.ok[slot, :n].tolist() == gold["ok"].tolist()
+    assert res_arrays.ldpc_errors[slot, :n].tolist() == gold["ldpc_errors"].tolist()
+    assert res_arrays.crc_extracted[slot, :n].tolist() == gold["crc_extracted"].tolist()
+    assert res_arrays.crc_calculated[slot, :n].tolist() == gold["crc_calculated"].tolist()
+    assert res_arrays.payload[slot, :n].tolist() == gold["payload"].tolist()
+
+
+def check_result_list(res, gold):
+    assert [list(m.payload) for m, *_ in res] == gold["res_payload"].tolist()
+    assert [m.hash for m, *_ in res] == gold["res_hash"].tolist()
+    np.testing.assert_array_equal([r[2] for r in res], gold["res_time_sec"])
+    np.testing.assert_array_equal([r[3] for r in res], gold["res_freq_hz"])
+    np.testing.assert_allclose([r[4] for r in res], gold["res_score"], rtol=0, atol=SCORE_TOL)
+
+
+@pytest.mark.parametrize("tag,kw", [
+    ("k20_s1", dict(max_candidates=20, min_score=1)),
+    ("k20_s3", dict(max_candidates=20, min_score=3)),
+    ("k20_s10", dict(max_candidates=20, min_score=10)),
+    ("k7_s2_it5", dict(max_candidates=7, min_score=2, max_iterations=5)),
+    ("band_time", dict(max_candidates=20, min_score=1.5, freq_min=300.0, freq_max=1200.0, time_min=0.2, time_max=14.5)),
+])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_c1_golden(c1_slot, tag, kw, dtype):
+    gold = golden_case(load_golden("c1.npz"), tag)
+    x = c1_slot.astype(dtype)                    # float32-representable: both dtypes carry identical values
+    batch = fd.decode_slots(x.reshape(1, -1), 12000, 2, 2, **kw)
+    check_against_gold(batch.arrays, gold)
+    res = fd.decode_ft8_message(x, 12000, bins_per_tone=2, steps_per_symbol=2, **kw)
+    check_result_list(res, gold)
+    for m, st, ts, fh, sc in res:
+        assert isinstance(m, fd.FT8Message) and isinstance(st, fd.FT8DecodeStatus) and len(m.payload) == 10
+
+
+def test_wav_fixture_golden():
+    g = load_golden("wav_fs20k.npz")
+    x = (g["samples_int16"].astype(np.float32) / 32767)
+    gold = golden_case(g, "f64")
+    res = fd.decode_ft8_message(x, int(g["fs"]), 2, 2, 20, 10, 20, freq_max=1000)
+    check_result_list(res, gold)
+    assert [bytes(m.payload).hex() for m, *_ in res] == ["aa0203040506070809f8"] * 3
+    assert [r[3] for r in res] == [550.0, 553.125, 546.875]
+
+
+@pytest.mark.parametrize("tag,kw", [
+    ("k2000_s3", dict(max_candidates=2000, min_score=3, freq_max=3100)),
+    ("k20_s3", dict(max_candidates=20, min_score=3, freq_max=3100)),
+])
+def test_c2_golden(tag, kw):
+    g = load_golden("c2.npz")
+    slot, payloads, *_ = synth.c2_slot()
+    gold = golden_case(g, tag)
+    batch = fd.decode_slots(slot.astype(np.float32).reshape(1, -1), 12000, 2, 2, max_iterations=20, **kw)
+    check_against_gold(batch.arrays, gold)
+    if tag == "k2000_s3":
+        decoded = batch.payload_sets()[0]
+        assert decoded == set(bytes(p) for p in gold["res_payload"]) and len(decoded & set(payloads)) >= 20
+
+
+@pytest.mark.parametrize("tag", ["fs6000", "fs10000_osr4", "fs3500", "fs12000_osr10", "fs32768"])
+def test_other_rates_golden(tag):
+    g = load_golden("rates.npz")
+    r = json.loads(str(g[tag + "__recipe"]))
+    slot = synth.make_slot(bytes(g[tag + "__tx_payload"]), seed=r["seed"], fs=r["fs"], f0=r["f0"], start_s=r["start"],
+                           snr_db=r["snr"], duration_s=r["dur"])
+    gold = golden_case(g, tag)
+    batch = fd.decode_slots(slot.reshape(1, -1), r["fs"], max_iterations=20, **r["kw"])
+    check_against_gold(batch.arrays, gold)
+    check_result_list(fd.decode_ft8_message(slot, r["fs"], max_iterations=20, **r["kw"]), gold)
+
+
+def test_batch_vs_oracle_c3(orc):
+    """Config C3 sample: 24 seeded slots decoded in one batch (several chunks) == oracle slot by slot."""
+    n = 24
+    slots, payloads = zip(*[synth.c3_slot(i) for i in range(n)])
+    waves = np.stack(slots).astype(np.float32)
+    batch = fd.decode_slots(waves, 12000, 2, 2, max_candidates=20, min_score=1, max_iterations=20, chunk_slots=7)
+    ref = orc.decode_batch(waves.astype(np.float64), 12000, 2, 2, 20, 1, 20, n_threads=8)
+    a = batch.arrays
+    hits = 0
+    for i in range(n):
+        assert int(a.n_cand[i]) == len(ref[i])
+        for c, r in enumerate(ref[i]):
+            assert (int(a.cand_time[i, c]), int(a.cand_freq[i, c])) == (r["abs_time"], r["abs_freq"])
+            assert abs(float(a.cand_score[i, c]) - r["score"]) < SCORE_TOL
+            assert bool(a.ok[i, c]) == r["ok"] and int(a.ldpc_errors[i, c]) == r["ldpc_errors"]
+            assert int(a.crc_extracted[i, c]) == r["crc_extracted"] and int(a.crc_calculated[i, c]) == r["crc_calculated"]
+            assert bytes(a.payload[i, c].numpy()) == r["payload"]
+        hits += payloads[i] in batch.payload_sets()[i]
+    assert hits >= n // 2          # round trip: most transmitted payloads come back (SNR -16..-4 dB)
+    # chunking must not change anything
+    again = fd.decode_slots(waves, 12000, 2, 2, max_candidates=20, min_score=1, max_iterations=20, chunk_slots=24)
+    for f in a.__dataclass_fields__:
+        assert torch.equal(getattr(a, f), getattr(again.arrays, f))
+
+
+def test_dropin_stage_functions(orc, c1_slot):
+    """ft8_find_candidates / ft8_sync_score / ft8_decode_candidate / ft8_extract_likelihood on a host waterfall."""
+    mag = orc.spectrogram_pos(c1_slot, 12000, 2, 2)
+    wf = fd.create_waterfall_from_spectrogram(mag, 2, 2)
+    assert wf.num_bins == 1920 and wf.num_blocks == 93
+    cands = fd.ft8_find_candidates(wf, 20, 1)
+    ct, cf, cs, _ = orc.ft8_find_candidates(mag, 2, 2, 20, 1)
+    assert [(c.abs_time, c.abs_freq) for c in cands] == list(zip(ct.tolist(), cf.tolist()))
+    assert abs(fd.ft8_sync_score(wf, cands[0]) - cs[0]) < 1e-12
+    ok, msg, st = fd.ft8_decode_candidate(wf, cands[0], 20)
+    assert ok and bytes(msg.payload) == synth.C1_PAYLOAD and msg.hash == 7997 and st.ldpc_errors == 0
+    ok2, msg2, st2 = fd.ft8_decode_candidate(wf, cands[1], 20)
+    r = orc.ft8_decode_candidate(mag, 2, 2, cands[1].abs_time, cands[1].abs_freq, 20)
+    assert ok2 == r["ok"] and st2.ldpc_errors == r["ldpc_errors"] and bytes(msg2.payload) == r["payload"]
+    l = np.zeros(174)
+    fd.ft8_extract_likelihood(wf, cands[0], l)
+    assert np.array_equal(l, orc.ft8_extract_likelihood(mag, 2, 2, cands[0].abs_time, cands[0].abs_freq))
+    with pytest.raises(ValueError):
+        fd.create_waterfall_from_spectrogram(np.zeros(5), 2, 2)
+
+
+def test_edge_cases():
+    assert fd.decode_ft8_message(np.zeros(180000), 12000) == []            # all scores 0 < 10
+    assert fd.decode_ft8_message(np.zeros(1000), 12000) == []              # shorter than one window
+    assert fd.decode_ft8_message(np.zeros(10), 12000) == []
+    assert fd.decode_ft8_message(np.zeros(30000), 12000, min_score=-5) == []   # too few blocks: empty search range
+    b = fd.decode_slots(np.zeros((0, 180000), dtype=np.float32), 12000)
+    assert len(b) == 0
+    with pytest.raises(NotImplementedError):
+        fd.decode_slots(np.zeros((1, 180000), dtype=np.float32), 12000, max_candidates=5000)
+    with pytest.raises(NotImplementedError):
+        sa.calculate_spectrogram(np.zeros(400000), 1_000_000)               # nfft 320000: beyond the smem FFT
+    # constant spectrogram with min_score <= 0: every score ties at 0.0 (the reference raises TypeError);
+    # the deterministic tie-break returns the first K positions in scan order
+    wf = fd.create_waterfall_from_spectrogram(np.zeros((120, 160)), 2, 2)
+    c = fd.ft8_find_candidates(wf, 5, 0)
+    assert [(x.abs_time, x.abs_freq) for x in c] == [(-20, i) for i in range(5)]

@@ -1,0 +1,139 @@
+"""Host-side logic of the Python mirror: mask arithmetic, types, byte utilities, the signal generator,
+and the multi-rank sharding helpers (gloo, world_size 2)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import load_golden
+from ft8_demodulator_b200 import dist as fdist, synth
+from ft8_demodulator_b200.ft8_demodulator import constants, crc, ft8_decode as fd, ftx_types, spectrogram_analyse as sa
+
+
+@pytest.mark.parametrize("fs,b,s,n", [(12000, 2, 2, 180000), (20000, 2, 2, 252800), (10e3, 4, 4, 140000), (32768, 2, 2, 442368),
+                                      (3500, 2, 2, 52500)])
+@pytest.mark.parametrize("lims", [(None, None, None, None), (300.0, 1200.0, 0.2, 14.5), (None, 1000, None, None),
+                                  (0, 3000, None, None), (550.0, None, 10, None), (None, None, None, 3.0),
+                                  (1e9, None, None, None), (None, None, 1e9, None), (3.125, 3.125, 0.16, 0.16)])
+def test_masks_match_oracle(orc, fs, b, s, n, lims):
+    g = fd.decode_geometry(n, fs, b, s, *lims)
+    o = orc.masks(fs, g["nperseg"], g["hop"], g["nfft"], g["T_all"], *lims)
+    got = (g["bin_lo"], g["bin_hi"], g["frame_lo"], g["frame_hi"])
+    if o[1] - o[0] <= 0:
+        assert got[1] - got[0] == 0
+    else:
+        assert got[:2] == o[:2]
+    if o[3] - o[2] <= 0:
+        assert got[3] - got[2] == 0
+    else:
+        assert got[2:] == o[2:]
+
+
+def test_axes_match_golden():
+    g = load_golden("c1.npz")
+    np.testing.assert_array_equal(sa.frequency_axis(3840, 12000), g["spec_f"])
+    np.testing.assert_array_equal(sa.time_axis(180000, 1920, 960, 12000), g["spec_t"])
+
+
+def test_types_and_constants():
+    wf = ftx_types.FT8Waterfall(mag=np.zeros((1920, 187)), time_osr=2, freq_osr=2)
+    assert wf.num_bins == 1920 and wf.num_blocks == 93
+    with pytest.raises(ValueError):
+        ftx_types.FT8Waterfall(mag=np.zeros(5), time_osr=2, freq_osr=2)
+    wf.mag[10 + 3 * 2, 4 + 5 * 2] = 7.0
+    assert ftx_types.FT8Candidate(wf, abs_time=4, abs_freq=10).get_log_power(5, 3) == 7.0
+    assert bytes(ftx_types.FT8Message().payload) == bytes(10) and ftx_types.FT8DecodeStatus().ldpc_errors == 0
+    assert len(constants.kFTX_LDPC_Nm) == 83 and len(constants.kFTX_LDPC_Mn) == 174
+    assert sum(constants.kFTX_LDPC_Num_rows) == 522 and sorted(set(constants.kFTX_LDPC_Num_rows)) == [6, 7]
+    H, G = constants.parity_check_matrix(), constants.generator_matrix()
+    cw = np.concatenate([np.eye(91, dtype=np.uint8), (G @ np.eye(91, dtype=np.int64) % 2).T.astype(np.uint8)], axis=1)
+    assert not ((H.astype(np.int64) @ cw.T.astype(np.int64)) % 2).any()
+
+
+def test_crc_and_pack_bits_against_reference_kat():
+    kat = load_golden("kat_encode.json")
+    for hx, k in kat.items():
+        a91 = bytearray(bytes.fromhex(k["a91"]))
+        assert crc.extract_crc(a91) == k["crc"]
+        buf = bytearray(a91[:10] + b"\0\0")
+        buf[9] &= 0xF8
+        assert crc.compute_crc(buf, 82) == k["crc"]
+        out = bytearray(12)
+        crc.add_crc(bytearray.fromhex(hx), out)
+        assert out == a91
+        bits = np.unpackbits(np.frombuffer(bytes.fromhex(k["codeword"]), dtype=np.uint8))[:174]
+        assert fd.pack_bits(bits, 91) == bytearray(bytes.fromhex(k["a91"]))
+    l = np.zeros(3)
+    fd.ft8_extract_symbol(np.array([1., 9., 2., 3., 4., 5., 6., 7.]), l)
+    assert l.tolist() == [7 - 9, 7 - 9, 9 - 5]      # s2 = wf[gray] = [1,9,3,2,5,6,4,7]
+
+
+def test_generator_known_answers():
+    it = synth.ft8_encode(np.frombuffer(bytes.fromhex("1c3f8a6ae207a1e39451"), dtype=np.uint8))
+    assert "".join(map(str, it)) == ("3140652" "07027413236410076024143535742" "3140652"
+                                     "47714340647105233673231511607" "3140652")
+    w = synth.ft8_generator(np.frombuffer(synth.C1_PAYLOAD, dtype=np.uint8), 12000, 500, 0)
+    assert len(w) == 151680 and abs(np.sqrt(np.mean(w ** 2)) - 0.7064115443739227) < 1e-12
+    llr, bits = synth.c5_llr(32, seed=1)
+    assert llr.shape == (32, 174) and np.allclose(llr.var(axis=1), 24.0)
+    H = constants.parity_check_matrix().astype(np.int64)
+    assert not ((H @ bits.T.astype(np.int64)) % 2).any()
+
+
+def test_torch_batch_generator_decodes_with_oracle(orc):
+    w, pl = synth.synth_batch_torch(3, torch.device("cpu"), seed=1234)
+    recs = orc.decode_batch(w.numpy().astype(np.float64), 12000, 2, 2, 20, 1, 20, n_threads=3)
+    hits = sum(any(r["ok"] and r["payload"] == bytes(pl[i]) for r in recs[i]) for i in range(3))
+    assert hits >= 2
+
+
+def test_shard_range():
+    for n in (0, 1, 7, 4096, 10 ** 6):
+        for world in (1, 2, 3, 8):
+            parts = [fdist.shard_range(n, r, world) for r in range(world)]
+            assert parts[0][0] == 0 and parts[-1][1] == n
+            assert all(parts[i][1] == parts[i + 1][0] for i in range(world - 1))
+            sizes = [hi - lo for lo, hi in parts]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        fdist.shard_range(10, 2, 2)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _gather_worker(rank, world, port, n_total, K):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    r, _, w = fdist.init_process_group("gloo")
+    lo, hi = fdist.shard_range(n_total, r, w)
+    rec = torch.zeros((hi - lo, K, fdist.RECORD_WIDTH), dtype=torch.int32)
+    rec[:, :, 4] = torch.arange(lo, hi, dtype=torch.int32)[:, None]      # slot id in the abs_time field
+    rec[:, :, 5] = torch.arange(K, dtype=torch.int32)[None, :]
+    allrec = fdist.gather_records(rec, n_total, r, w)
+    assert allrec.shape == (n_total, K, fdist.RECORD_WIDTH)
+    assert torch.equal(allrec[:, 0, 4], torch.arange(n_total, dtype=torch.int32))
+    assert torch.equal(allrec[3, :, 5], torch.arange(K, dtype=torch.int32))
+    dist.destroy_process_group()
+
+
+def test_gather_records_world2_gloo():
+    """N > 1 path on CPU: uneven shards, all_gather of the fixed-size decode records, slot order preserved."""
+    mp.spawn(_gather_worker, args=(2, _free_port(), 11, 4), nprocs=2, join=True)
+
+
+def test_pack_records_layout():
+    from ft8_demodulator_b200 import engine
+    o = engine.alloc_slot_decodes(2, 3, torch.device("cpu"))
+    o.ok[1, 2] = 1
+    o.cand_time[1, 2] = -7
+    o.payload[1, 2] = torch.arange(10, dtype=torch.uint8)
+    rec = fdist.pack_records(o)
+    assert rec.shape == (2, 3, 16) and rec[1, 2, 0] == 1 and rec[1, 2, 4] == -7 and rec[1, 2, 6:].tolist() == list(range(10))
