@@ -73,9 +73,9 @@ struct StageScope {
 static int default_chunk_slots(int64_t per_slot_bytes) {
     // Enough slots per launch to fill 148 SMs several times over in every stage; the kernels are bound by
     // the FP64 pipe, not HBM, so L2 residency of the chunk's spectrogram is secondary.
-    int64_t c = (512ll << 20) / (per_slot_bytes > 0 ? per_slot_bytes : 1);
+    int64_t c = (2048ll << 20) / (per_slot_bytes > 0 ? per_slot_bytes : 1);
     if (c < 1) c = 1;
-    if (c > 4096) c = 4096;
+    if (c > 512) c = 512;
     return (int)c;
 }
 

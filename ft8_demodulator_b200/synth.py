@@ -61,6 +61,8 @@ def crc14_bits(payload_bits: np.ndarray) -> np.ndarray:
 def add_crc(payload10) -> np.ndarray:
     """77-bit payload (10 bytes, low 3 bits of byte 9 ignored) -> a91 (12 bytes). crc.py:25-47."""
     a91 = np.zeros(12, dtype=np.uint8)
+    if isinstance(payload10, (bytes, bytearray)):
+        payload10 = np.frombuffer(bytes(payload10), dtype=np.uint8)
     a91[:10] = np.asarray(payload10, dtype=np.uint8)[:10]
     a91[9] &= 0xF8
     c = crc14(bytes(a91), 96 - 14)

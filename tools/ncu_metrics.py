@@ -1,0 +1,20 @@
+#!/usr/bin/env python
+"""Compact per-kernel table from `ncu -i X.ncu-rep --page raw --csv` output (stdin or file)."""
+import csv
+import sys
+
+rows = list(csv.reader(open(sys.argv[1]) if len(sys.argv) > 1 else sys.stdin))
+hdr, units, data = rows[0], rows[1], rows[2:]
+ix = {h: i for i, h in enumerate(hdr)}
+want = [
+    "Kernel Name", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+    "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
+    "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+]
+for w in want:
+    if w in ix:
+        print("%-72s %-16s %s" % (w, units[ix[w]], " | ".join(r[ix[w]][:30] for r in data)))
