@@ -37,7 +37,7 @@ struct StftPlan {
     size_t smem = 0;
     // canonical-geometry fast path (nperseg 1920, nfft 3840): extra twiddle tables for stft1920_kernel
     int fast = 0;
-    double2 *tw2 = nullptr, *tw3 = nullptr;
+    double2 *tw2 = nullptr, *tw3 = nullptr, *logtab = nullptr;
 };
 
 struct StftArgs {
@@ -339,6 +339,13 @@ static int get_plan(int nperseg, int nfft, const StftPlan **out) {
                 long double ang = -two_pi * (long double)(t * j) / 1920.0L;
                 t3[t * 240 + j] = make_double2((double)cosl(ang), (double)sinl(ang));
             }
+        std::vector<double2> lt(128);
+        for (int i = 0; i < 128; ++i) {
+            const double inv = 1.0 / (1.0 + ((double)i + 0.5) / 128.0);
+            lt[i] = make_double2(inv, (double)(-10.0L * log10l((long double)inv)));
+        }
+        FT8B_CUDA_TRY(cudaMalloc(&p.logtab, sizeof(double2) * lt.size()));
+        FT8B_CUDA_TRY(cudaMemcpy(p.logtab, lt.data(), sizeof(double2) * lt.size(), cudaMemcpyHostToDevice));
         FT8B_CUDA_TRY(cudaMalloc(&p.tw2, sizeof(double2) * t2.size()));
         FT8B_CUDA_TRY(cudaMalloc(&p.tw3, sizeof(double2) * t3.size()));
         FT8B_CUDA_TRY(cudaMemcpy(p.tw2, t2.data(), sizeof(double2) * t2.size(), cudaMemcpyHostToDevice));
@@ -358,6 +365,7 @@ int release_plans() {
         cudaFree(kv.second.win);
         cudaFree(kv.second.tw2);
         cudaFree(kv.second.tw3);
+        cudaFree(kv.second.logtab);
     }
     g_plans.clear();
     return 0;
@@ -382,12 +390,25 @@ int stft_db(const void *wave, int wave_dtype, int64_t n_slots, int64_t n_samples
     if (plan->fast && !(force_generic && force_generic[0] == '1')) {
         Stft1920Args f;
         f.wave = wave; f.n_slots = n_slots; f.slot_stride = slot_stride; f.hop = hop;
-        f.win = plan->win; f.tw2 = plan->tw2; f.tw3 = plan->tw3; f.twpost = plan->twpost; f.scale = plan->scale;
+        f.win = plan->win; f.tw2 = plan->tw2; f.tw3 = plan->tw3; f.twpost = plan->twpost; f.logtab = plan->logtab; f.scale = plan->scale;
         f.bin_lo = bin_lo; f.bin_hi = bin_hi; f.frame_lo = frame_lo; f.frames_out = frame_hi - frame_lo; f.mag = mag;
         const int64_t items = n_slots * f.frames_out;
         int64_t g1920 = items < 148 * 32 ? items : 148 * 32;
-        if (wave_dtype == FT8B_DTYPE_F32) stft1920_kernel<float><<<(unsigned)g1920, kStft1920Threads, 0, stream>>>(f);
-        else stft1920_kernel<double><<<(unsigned)g1920, kStft1920Threads, 0, stream>>>(f);
+        static const int mb = [] { const char *e = getenv("FT8B_STFT_MINBLOCKS"); return e ? atoi(e) : 4; }();
+        // vector loads of sample pairs need every frame start to be 2-element aligned
+        const size_t pair_bytes = wave_dtype == FT8B_DTYPE_F32 ? 8 : 16;
+        const bool vec = (reinterpret_cast<uintptr_t>(wave) % pair_bytes == 0) && (slot_stride % 2 == 0) && (hop % 2 == 0);
+#define FT8B_STFT1920(T, MB)                                                                              \
+    do {                                                                                                  \
+        if (vec) stft1920_kernel<T, MB, true><<<(unsigned)g1920, kStft1920Threads, 0, stream>>>(f);      \
+        else stft1920_kernel<T, MB, false><<<(unsigned)g1920, kStft1920Threads, 0, stream>>>(f);         \
+    } while (0)
+        if (wave_dtype == FT8B_DTYPE_F32) {
+            if (mb == 5) FT8B_STFT1920(float, 5); else FT8B_STFT1920(float, 4);
+        } else {
+            if (mb == 5) FT8B_STFT1920(double, 5); else FT8B_STFT1920(double, 4);
+        }
+#undef FT8B_STFT1920
         FT8B_LAUNCH_CHECK("stft1920_kernel");
         return 0;
     }

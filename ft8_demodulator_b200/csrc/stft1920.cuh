@@ -26,6 +26,7 @@ struct Stft1920Args {
     const double2 *tw2;       // [16][15]  exp(-2*pi*i*t*k/240)
     const double2 *tw3;       // [8][240]  exp(-2*pi*i*t*j/1920)
     const double2 *twpost;    // [1921]    exp(-2*pi*i*k/3840)
+    const double2 *logtab;    // [128]     (1/c_i, 10*log10(c_i)), c_i = 1/fl(1/(1+(i+0.5)/128))
     double scale;
     int bin_lo, bin_hi;
     int64_t frame_lo, frames_out;
@@ -33,6 +34,27 @@ struct Stft1920Args {
 };
 
 namespace f1920 {
+
+// Butterfly / polynomial constants live in constant memory: DFMA/DMUL read them as c[bank][offset]
+// operands, whereas 64-bit immediates would need two UMOV each, every time they are used.
+__device__ __constant__ double kK[40] = {
+    /* 0 */ 0.86602540378443864676,   // sin(2*pi/3)
+    /* 1 */ 0.30901699437494742410,   // cos(2*pi/5)
+    /* 2 */ -0.80901699437494742410,  // cos(4*pi/5)
+    /* 3 */ 0.95105651629515357212,   // sin(2*pi/5)
+    /* 4 */ 0.58778525229247312917,   // sin(4*pi/5)
+    /* 5 */ 0.91354545764260089550, /* 6 */ 0.40673664307580020775,    // cos, sin(2*pi*1/15)
+    /* 7 */ 0.66913060635885821383, /* 8 */ 0.74314482547739423501,    // 2/15
+    /* 9 */ -0.10452846326765347140, /* 10 */ 0.99452189536827333692,  // 4/15
+    /* 11 */ -0.97814760073380563793, /* 12 */ -0.20791169081775933710, // 8/15
+    /* 13 */ 0.92387953251128675613, /* 14 */ 0.38268343236508977173,  // cos, sin(pi/8)
+    /* 15 */ 0.70710678118654752440,  // sqrt(1/2)
+    /* 16 */ 0.62042067417029334,     // (10/ln10)/7 ... alternating-sign Taylor coefficients of 10*log10(1+r)
+    /* 17 */ -0.72382411986534223, /* 18 */ 0.86858894383841068, /* 19 */ -1.0857361797980134,
+    /* 20 */ 1.4476482397306845, /* 21 */ -2.1714723595960267, /* 22 */ 4.3429448190325183,
+    /* 23 */ 3.0102999566398120,      // 10*log10(2)
+    /* 24 */ 1e-12,
+};
 
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
     return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
@@ -54,7 +76,7 @@ __device__ __forceinline__ void bf4(double2 &a, double2 &b, double2 &c, double2 
     d = cadd(d02, mul_pi(d13));
 }
 __device__ __forceinline__ void bf3(double2 &a, double2 &b, double2 &c) {
-    const double kS = 0.86602540378443864676;
+    const double kS = kK[0];
     const double2 t1 = cadd(b, c);
     const double2 t2 = make_double2(a.x - 0.5 * t1.x, a.y - 0.5 * t1.y);
     const double2 d = csub(b, c);
@@ -64,8 +86,7 @@ __device__ __forceinline__ void bf3(double2 &a, double2 &b, double2 &c) {
     c = cadd(t2, mul_pi(t3));
 }
 __device__ __forceinline__ void bf5(double2 &u0, double2 &u1, double2 &u2, double2 &u3, double2 &u4) {
-    const double c1 = 0.30901699437494742410, c2 = -0.80901699437494742410;
-    const double s1 = 0.95105651629515357212, s2 = 0.58778525229247312917;
+    const double c1 = kK[1], c2 = kK[2], s1 = kK[3], s2 = kK[4];
     const double2 a = u0;
     const double2 t1 = cadd(u1, u4), t2 = cadd(u2, u3), t3 = csub(u1, u4), t4 = csub(u2, u3);
     const double2 m1 = make_double2(a.x + c1 * t1.x + c2 * t2.x, a.y + c1 * t1.y + c2 * t2.y);
@@ -82,12 +103,8 @@ __device__ __forceinline__ void bf5(double2 &u0, double2 &u1, double2 &u2, doubl
 // 15-point DFT, t = 3a + b in, f = q + 5r out (in place, natural order on both sides)
 __device__ __forceinline__ void bf15(double2 (&x)[15]) {
     // cos/sin(2*pi*m/15)
-    const double C1 = 0.91354545764260089550, S1 = 0.40673664307580020775;
-    const double C2 = 0.66913060635885821383, S2 = 0.74314482547739423501;
-    const double C3 = 0.30901699437494742410, S3 = 0.95105651629515357212;
-    const double C4 = -0.10452846326765347140, S4 = 0.99452189536827333692;
-    const double C6 = -0.80901699437494742410, S6 = 0.58778525229247312917;
-    const double C8 = -0.97814760073380563793, S8 = -0.20791169081775933710;
+    const double C1 = kK[5], S1 = kK[6], C2 = kK[7], S2 = kK[8], C3 = kK[1], S3 = kK[3];
+    const double C4 = kK[9], S4 = kK[10], C6 = kK[2], S6 = kK[4], C8 = kK[11], S8 = kK[12];
     bf5(x[0], x[3], x[6], x[9], x[12]);     // b = 0 : Y0[q] in x[3q]
     bf5(x[1], x[4], x[7], x[10], x[13]);    // b = 1 : Y1[q] in x[3q+1]
     bf5(x[2], x[5], x[8], x[11], x[14]);    // b = 2 : Y2[q] in x[3q+2]
@@ -106,7 +123,7 @@ __device__ __forceinline__ constexpr int out15(int pos) { return (pos / 3) + 5 *
 
 // 16-point DFT, t = 4a + b in, f = q + 4r out; after the call x[4q + r] = X[q + 4r]
 __device__ __forceinline__ void bf16(double2 (&x)[16]) {
-    const double C = 0.92387953251128675613, S = 0.38268343236508977173, H = 0.70710678118654752440;
+    const double C = kK[13], S = kK[14], H = kK[15];
     bf4(x[0], x[4], x[8], x[12]);     // b = 0 : Y0[q] in x[4q]
     bf4(x[1], x[5], x[9], x[13]);     // b = 1 : Y1[q] in x[4q+1]
     bf4(x[2], x[6], x[10], x[14]);
@@ -124,7 +141,7 @@ __device__ __forceinline__ constexpr int out16(int pos) { return (pos / 4) + 4 *
 
 // 8-point DFT in place, natural order in and out
 __device__ __forceinline__ void bf8(double2 (&a)[8]) {
-    const double H = 0.70710678118654752440;
+    const double H = kK[15];
     double2 b0 = cadd(a[0], a[4]), b1 = cadd(a[1], a[5]), b2 = cadd(a[2], a[6]), b3 = cadd(a[3], a[7]);
     double2 c0 = csub(a[0], a[4]), c1 = csub(a[1], a[5]), c2 = csub(a[2], a[6]), c3 = csub(a[3], a[7]);
     c1 = cmulc(c1, H, H);
@@ -135,27 +152,64 @@ __device__ __forceinline__ void bf8(double2 (&a)[8]) {
     a[0] = b0; a[1] = c0; a[2] = b1; a[3] = c1; a[4] = b2; a[5] = c2; a[6] = b3; a[7] = c3;
 }
 
-__device__ __forceinline__ double to_db(double re, double im, double scale) {
-    return 10.0 * log10(1e-12 + (re * re + im * im) * scale);
+// 10*log10(v) for finite v >= 1e-12 without the libdevice log10 (a division, ~35 FP64 instructions and a
+// slow-path branch per element).  v = 2^e * m, m in [1,2); i = top 7 mantissa bits; r = m * (1/c_i) - 1 with
+// |r| <= 2^-8; 10*log10(v) = e*10*log10(2) + 10*log10(c_i) + (10/ln 10) * (r - r^2/2 + ... + r^7/7).
+// Max error 2.4e-14 dB against extended precision over [1e-12, 1e4] (np.log10 itself: 1.6e-14 dB).
+__device__ __noinline__ double slow_db(double v) { return 10.0 * log10(v); }
+
+__device__ __forceinline__ double fast_db(double v, const double2 *__restrict__ tab) {
+    const long long bits = __double_as_longlong(v);
+    if (bits >= 0x7ff0000000000000LL || bits <= 0) return slow_db(v);          // inf / NaN / non-positive: libdevice path
+    const int e = (int)(bits >> 52) - 1023;
+    const int i = (int)(bits >> 45) & 127;
+    const double m = __longlong_as_double((bits & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);
+    const double2 t = tab[i];
+    const double r = fma(m, t.x, -1.0);
+    double p = kK[16];                              // (10/ln10)/7
+    p = fma(p, r, kK[17]);                          // -(10/ln10)/6
+    p = fma(p, r, kK[18]);                          //  (10/ln10)/5
+    p = fma(p, r, kK[19]);                          // -(10/ln10)/4
+    p = fma(p, r, kK[20]);                          //  (10/ln10)/3
+    p = fma(p, r, kK[21]);                          // -(10/ln10)/2
+    p = fma(p, r, kK[22]);                          //  (10/ln10)
+    return fma(r, p, fma((double)e, kK[23], t.y));
 }
 
-// Untangle the pair (Z[k], Z[M-k]) of the packed transform and emit dB for bins k and M-k.
-__device__ __forceinline__ void emit_pair(double2 z, double2 zr, int k, const Stft1920Args &a, double *out) {
+// Untangle the pair (Z[k], Z[M-k]) of the packed transform and emit dB for bins k and M-k
+// (spectrogram_analyse.py:59-60: 10*log10(1e-12 + |S|), S = |X|^2 / (sum w)^2).
+__device__ __forceinline__ void emit_pair(double2 z, double2 zr, int k, const Stft1920Args &a, double *out,
+                                          const double2 *__restrict__ tab) {
     const double2 zc = make_double2(zr.x, -zr.y);
     const double2 e = make_double2(0.5 * (z.x + zc.x), 0.5 * (z.y + zc.y));
     const double2 p = cmul(__ldg(&a.twpost[k]), csub(z, zc));
     const int k2 = kM1920 - k;
-    if (k >= a.bin_lo && k < a.bin_hi) out[k - a.bin_lo] = to_db(e.x + 0.5 * p.y, e.y - 0.5 * p.x, a.scale);
-    if (k2 != k && k2 >= a.bin_lo && k2 < a.bin_hi) out[k2 - a.bin_lo] = to_db(e.x - 0.5 * p.y, e.y + 0.5 * p.x, a.scale);
+    const double re1 = e.x + 0.5 * p.y, im1 = e.y - 0.5 * p.x;
+    const double re2 = e.x - 0.5 * p.y, im2 = e.y + 0.5 * p.x;
+    if (k >= a.bin_lo && k < a.bin_hi) out[k - a.bin_lo] = fast_db(kK[24] + (re1 * re1 + im1 * im1) * a.scale, tab);
+    if (k2 != k && k2 >= a.bin_lo && k2 < a.bin_hi)
+        out[k2 - a.bin_lo] = fast_db(kK[24] + (re2 * re2 + im2 * im2) * a.scale, tab);
 }
 
 }  // namespace f1920
 
-template <typename WaveT>
-__global__ void __launch_bounds__(kStft1920Threads, 4) stft1920_kernel(const Stft1920Args a) {
+// samples 2n, 2n+1 as one vector load (the caller guarantees 8/16-byte alignment when VEC is set)
+__device__ __forceinline__ double2 load_pair(const float *x, int n) {
+    const float2 v = __ldg(reinterpret_cast<const float2 *>(x) + n);
+    return make_double2((double)v.x, (double)v.y);
+}
+__device__ __forceinline__ double2 load_pair(const double *x, int n) { return __ldg(reinterpret_cast<const double2 *>(x) + n); }
+
+// MB = CTAs per SM the register allocation must allow (4: 128 regs, 5: 96 regs, 6: 80 regs)
+template <typename WaveT, int MB, bool VEC>
+__global__ void __launch_bounds__(kStft1920Threads, MB) stft1920_kernel(const Stft1920Args a) {
     using namespace f1920;
     __shared__ double2 s[kM1920];
+    __shared__ double2 sp[16];
+    __shared__ double2 logtab[128];
     const int tid = threadIdx.x;
+    logtab[tid] = __ldg(&a.logtab[tid]);
+    __syncthreads();
     const int64_t n_items = a.n_slots * a.frames_out;
     const int Fout = a.bin_hi - a.bin_lo;
     for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -170,8 +224,13 @@ __global__ void __launch_bounds__(kStft1920Threads, 4) stft1920_kernel(const Stf
             for (int t = 0; t < 8; ++t) {
                 const int n = tid + 128 * t;
                 if (t < 7 || tid < 64) {
-                    const double w0 = __ldg(&a.win[2 * n]), w1 = __ldg(&a.win[2 * n + 1]);
-                    u[t] = make_double2(w0 * (double)x[2 * n], w1 * (double)x[2 * n + 1]);
+                    const double2 w = __ldg(reinterpret_cast<const double2 *>(a.win) + n);
+                    if (VEC) {
+                        const auto xv = load_pair(x, n);
+                        u[t] = make_double2(w.x * xv.x, w.y * xv.y);
+                    } else {
+                        u[t] = make_double2(w.x * (double)x[2 * n], w.y * (double)x[2 * n + 1]);
+                    }
                 } else {
                     u[t] = make_double2(0.0, 0.0);
                 }
@@ -203,9 +262,11 @@ __global__ void __launch_bounds__(kStft1920Threads, 4) stft1920_kernel(const Stf
         }
         __syncthreads();
         // ---------------- P3: radix 8, Ns = 240, paired butterflies + untangling + dB store
-        if (tid >= 1 && tid < 120) {
+        // thread i in 1..119 owns butterflies (i, 240-i); thread 120 owns the two self-paired ones (0, 120) and
+        // hands their outputs to lanes 120..127 through `sp` so no warp runs a second, divergent copy of the pass.
+        if (tid >= 1 && tid <= 120) {
             double2 u1[8], u2[8];
-            const int j1 = tid, j2 = 240 - tid;
+            const int j1 = (tid == 120) ? 0 : tid, j2 = (tid == 120) ? 120 : 240 - tid;
 #pragma unroll
             for (int t = 0; t < 8; ++t) { u1[t] = s[j1 + 240 * t]; u2[t] = s[j2 + 240 * t]; }
 #pragma unroll
@@ -215,21 +276,25 @@ __global__ void __launch_bounds__(kStft1920Threads, 4) stft1920_kernel(const Stf
             }
             bf8(u1);
             bf8(u2);
+            if (tid < 120) {
 #pragma unroll
-            for (int t = 0; t < 8; ++t) emit_pair(u1[t], u2[7 - t], j1 + 240 * t, a, out);
-        } else if (tid == 0) {
-            double2 u0[8], um[8];
+                for (int t = 0; t < 8; ++t) emit_pair(u1[t], u2[7 - t], j1 + 240 * t, a, out, logtab);
+            } else {
 #pragma unroll
-            for (int t = 0; t < 8; ++t) { u0[t] = s[240 * t]; um[t] = s[120 + 240 * t]; }
-#pragma unroll
-            for (int t = 1; t < 8; ++t) um[t] = cmul(um[t], __ldg(&a.tw3[t * 240 + 120]));
-            bf8(u0);
-            bf8(um);
-            emit_pair(u0[0], u0[0], 0, a, out);                                  // bins 0 and 1920
-#pragma unroll
-            for (int t = 1; t <= 4; ++t) emit_pair(u0[t], u0[8 - t], 240 * t, a, out);
-#pragma unroll
-            for (int t = 0; t < 4; ++t) emit_pair(um[t], um[7 - t], 120 + 240 * t, a, out);
+                for (int t = 0; t < 8; ++t) { sp[t] = u1[t]; sp[8 + t] = u2[t]; }
+            }
+        }
+        if (tid >= 96) {          // warp 3
+            __syncwarp();
+            if (tid >= 120) {
+                // 9 self-pairs: q = 0..4 -> (Z[240q], Z[1920-240q]); q = 5..8 -> (Z[120+240t], Z[1800-240t]), t = q-5
+                for (int q = tid - 120; q < 9; q += 8) {
+                    const int t = (q < 5) ? q : q - 5;
+                    const double2 z = (q < 5) ? sp[t] : sp[8 + t];
+                    const double2 zr = (q < 5) ? sp[(8 - t) & 7] : sp[15 - t];
+                    emit_pair(z, zr, (q < 5) ? 240 * t : 120 + 240 * t, a, out, logtab);
+                }
+            }
         }
         __syncthreads();   // s is rewritten by the next frame's P1
     }

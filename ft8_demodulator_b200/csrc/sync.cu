@@ -17,6 +17,7 @@
 // Loads are coalesced (adjacent f = adjacent bins) and every value is fetched once per tone offset
 // from L1/L2; the spectrogram is read from HBM once.
 #include <cmath>
+#include <cuda_pipeline.h>
 
 #include "common.cuh"
 
@@ -48,96 +49,146 @@ __device__ __forceinline__ int sync_num_comparisons(int u, int nb) {
     return n;
 }
 
+// One symbol step of the walk.  cur/nxt hold the 8 tone bins of columns g and g+1; HAS_NEXT is false only
+// for the last column (no later neighbour).
+template <bool HAS_NEXT>
+__device__ __forceinline__ double sync_step(const double (&cur)[8], const double (&nxt)[8], double (&dtprev)[7],
+                                            double (&acc)[6]) {
+    // dhi[tau] = A[tau] - A[tau+1]:  p - hi = dhi[tau],  p - lo = -dhi[tau-1]
+    double dhi[7], dt[7];
+#pragma unroll
+    for (int tau = 0; tau < 7; ++tau) dhi[tau] = __dsub_rn(cur[tau], cur[tau + 1]);
+    // dt[tau] = A[g][tau] - A[g+1][tau] = (p - later); (p - earlier) at the next step is -dt[tau]
+    if (HAS_NEXT) {
+#pragma unroll
+        for (int tau = 0; tau < 7; ++tau) dt[tau] = __dsub_rn(cur[tau], nxt[tau]);
+    }
+    // cell sums in the reference's order: (p-lo) + (p-hi) + (p-earlier) + (p-later)   (ft8_decode.py:79-94)
+    double G[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+        const int tau = (k == 0) ? 3 : (k == 1) ? 1 : (k == 2) ? 4 : (k == 3) ? 0 : (k == 4) ? 6 : (k == 5) ? 5 : 2;
+        double v = (tau > 0) ? __dadd_rn(-dhi[tau - 1], dhi[tau]) : dhi[0];
+        if (k > 0) v = __dadd_rn(v, dtprev[tau]);              // 0 at the first column
+        if (k < 6 && HAS_NEXT) v = __dadd_rn(v, dt[tau]);
+        G[k] = v;
+    }
+    if (HAS_NEXT) {
+#pragma unroll
+        for (int tau = 0; tau < 7; ++tau) dtprev[tau] = -dt[tau];
+    }
+    // rotate the block accumulators: acc[k] = S7(h = g-k) through cell k; S7(g-6) completes
+    const double done = __dadd_rn(acc[5], G[6]);
+#pragma unroll
+    for (int k = 5; k >= 1; --k) acc[k] = __dadd_rn(acc[k - 1], G[k]);
+    acc[0] = G[0];
+    return done;
+}
+
+// add a finished block sum S7(h) into the scores it belongs to: u = h+10 (m=0), h-26 (m=1), h-62 (m=2)
+__device__ __forceinline__ void sync_scatter(double *scp, int h, int nu, double v) {
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+        const unsigned u = (unsigned)(h + 10 - m * kSyncOffset);
+        if (u < (unsigned)nu) scp[u * kSyncThreads] = __dadd_rn(scp[u * kSyncThreads], v);
+    }
+}
+
+constexpr int kSyncStages = 5;   // spectrogram columns staged per warp: 2 in use + 3 in flight
+
+// Stage column `g` (clamped to the last one) of this warp's frequency strip into its ring slot with cp.async:
+// `w` values starting at bin f0, 8 bytes each, one or two per lane.  Every lane commits exactly one group per call.
+__device__ __forceinline__ void sync_stage_column(double *ring, int ring_w, const double *col0, int64_t rowstep, int g,
+                                                  int last, int w, int f_room, int lane) {
+    const int gc = g < last ? g : last;
+    const double *src = col0 + rowstep * gc;
+    double *dst = ring + (g % kSyncStages) * ring_w;
+    for (int it = 0, i = lane; it < (w + 31) / 32; ++it, i += 32)
+        if (i < w && i < f_room) __pipeline_memcpy_async(dst + i, src + i, 8);
+    __pipeline_commit();
+}
+
+template <int B>
 __global__ void __launch_bounds__(kSyncThreads) sync_scores_kernel(const SyncArgs a) {
-    extern __shared__ double sc[];            // [nu][kSyncThreads] running score sums, then int ncmp[nu]
-    const int tid = threadIdx.x;
+    extern __shared__ double sc[];   // [nu][kSyncThreads] score sums | ring[4 warps][kSyncStages][ring_w] | int ncmp[nu]
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int f = blockIdx.x * kSyncThreads + tid;
     const int rho = blockIdx.y;
     const int64_t slot = blockIdx.z;
-    const int nb = a.nb, nu = a.nu, s = a.s, b = a.b;
+    const int nb = a.nb, nu = a.nu, s = a.s;
+    const int bo = (B > 0) ? B : a.b;
+    const int ring_w = 32 + 7 * bo;                     // bins a warp touches per column
+    double *ring = sc + (size_t)nu * kSyncThreads + (size_t)wid * kSyncStages * ring_w;
+    int *ncmp = reinterpret_cast<int *>(sc + (size_t)nu * kSyncThreads + (size_t)(kSyncThreads / 32) * kSyncStages * ring_w);
+    for (int u = tid; u < nu; u += kSyncThreads) ncmp[u] = sync_num_comparisons(u, nb);
+    double *scp = sc + tid;
+    for (int u = 0; u < nu; ++u) scp[u * kSyncThreads] = 0.0;
+    __syncthreads();
+    const int f_warp = blockIdx.x * kSyncThreads + wid * 32;
+    if (f_warp >= a.nf) return;                          // whole warp beyond the last candidate frequency
     const bool active = f < a.nf;
 
-    int *ncmp = reinterpret_cast<int *>(sc + (size_t)nu * kSyncThreads);   // comparisons per u
-    for (int u = tid; u < nu; u += kSyncThreads) ncmp[u] = sync_num_comparisons(u, nb);
-    for (int u = 0; u < nu; ++u) sc[u * kSyncThreads + tid] = 0.0;
-    __syncthreads();
-
-    const double *base = a.mag + slot * (int64_t)a.T * a.F + f;   // + col*F + tau*b
-
+    // column g of this phase is waterfall column rho + s*g (ftx_types.py:45-47 with time_osr = s)
+    const double *col0 = a.mag + slot * (int64_t)a.T * a.F + (int64_t)rho * a.F + f_warp;
+    const int64_t rowstep = (int64_t)s * a.F;
+    const int f_room = a.F - f_warp;                     // bins left in the row from f_warp on
+    const int last = nb - 1;
+    double ca[8], cb[8], dtprev[7], acc[6];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) dtprev[k] = 0.0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) acc[k] = 0.0;
+    // prologue: columns 0 .. kSyncStages-2 in flight
+#pragma unroll
+    for (int g = 0; g < kSyncStages - 1; ++g) sync_stage_column(ring, ring_w, col0, rowstep, g, last, ring_w, f_room, lane);
+    __pipeline_wait_prior(kSyncStages - 2);              // column 0 has landed
+    __syncwarp();
     if (active) {
-        // register state: cur[tau] = A[g][f+tau*b], nxt[tau] = A[g+1][...]
-        double cur[8], nxt[8], dtprev[7], acc[7];
 #pragma unroll
-        for (int k = 0; k < 7; ++k) { dtprev[k] = 0.0; acc[k] = 0.0; }
-        {
-            const double *row = base + (int64_t)rho * a.F;   // g = 0 -> col = rho
+        for (int tau = 0; tau < 8; ++tau) ca[tau] = ring[lane + tau * bo];
+    }
+    // Steady state, unrolled by two so `cur`/`nxt` swap by renaming.  At step g: stage column g+4, wait until
+    // column g+1 has landed (3 younger groups may still be in flight), read it, do the arithmetic.
+#define FT8B_SYNC_STEP(CUR, NXT, G, HASNEXT)                                                                  \
+    do {                                                                                                      \
+        __syncwarp();                                                                                         \
+        sync_stage_column(ring, ring_w, col0, rowstep, (G) + kSyncStages - 1, last, ring_w, f_room, lane);    \
+        __pipeline_wait_prior(kSyncStages - 2);                                                               \
+        __syncwarp();                                                                                         \
+        if (active) {                                                                                         \
+            if (HASNEXT) {                                                                                    \
+                const double *rp_ = ring + (((G) + 1) % kSyncStages) * ring_w + lane;                         \
+                _Pragma("unroll") for (int tau = 0; tau < 8; ++tau) NXT[tau] = rp_[tau * bo];                 \
+            }                                                                                                 \
+            sync_scatter(scp, (G)-6, nu, sync_step<HASNEXT>(CUR, NXT, dtprev, acc));                          \
+        }                                                                                                     \
+    } while (0)
+    int g = 0;
+    for (; g + 2 <= last; g += 2) {
+        FT8B_SYNC_STEP(ca, cb, g, true);
+        FT8B_SYNC_STEP(cb, ca, g + 1, true);
+    }
+    if (g < last) {                                      // one leftover step with a successor
+        FT8B_SYNC_STEP(ca, cb, g, true);
 #pragma unroll
-            for (int tau = 0; tau < 8; ++tau) nxt[tau] = __ldg(row + tau * b);
-        }
-        for (int g = 0; g < nb; ++g) {
+        for (int tau = 0; tau < 8; ++tau) ca[tau] = cb[tau];
+        ++g;
+    }
+    FT8B_SYNC_STEP(ca, cb, g, false);                    // g == last
+#undef FT8B_SYNC_STEP
+    __pipeline_wait_prior(0);
+    if (!active) return;
+    // partial blocks that run past the last symbol: h = nb-6 .. nb-1 live in acc[5] .. acc[0]
 #pragma unroll
-            for (int tau = 0; tau < 8; ++tau) cur[tau] = nxt[tau];
-            const bool has_next = (g + 1 < nb);
-            if (has_next) {
-                const double *row = base + (int64_t)(rho + s * (g + 1)) * a.F;
-#pragma unroll
-                for (int tau = 0; tau < 8; ++tau) nxt[tau] = __ldg(row + tau * b);
-            }
-            // dhi[tau] = A[tau] - A[tau+1]  (tau 0..6);  p - lo = -dhi[tau-1],  p - hi = dhi[tau]
-            double dhi[7], dt[7];
-#pragma unroll
-            for (int tau = 0; tau < 7; ++tau) dhi[tau] = __dsub_rn(cur[tau], cur[tau + 1]);
-            // dt[tau] = A[g][tau] - A[g+1][tau]  = (p - later);  (p - earlier) at g+1 is -dt[tau]
-#pragma unroll
-            for (int tau = 0; tau < 7; ++tau) dt[tau] = has_next ? __dsub_rn(cur[tau], nxt[tau]) : 0.0;
-            // cell sums G_k in the reference's order: (p-lo) + (p-hi) + (p-earlier) + (p-later)
-            double G[7];
-#pragma unroll
-            for (int k = 0; k < 7; ++k) {
-                const int tau = (k == 0) ? 3 : (k == 1) ? 1 : (k == 2) ? 4 : (k == 3) ? 0 : (k == 4) ? 6 : (k == 5) ? 5 : 2;
-                double v;
-                if (tau > 0) v = __dadd_rn(-dhi[tau - 1], dhi[tau]);     // ft8_decode.py:79-85
-                else v = dhi[0];
-                if (k > 0) v = __dadd_rn(v, dtprev[tau]);                // :88-90 (dtprev is 0 at g == 0)
-                if (k < 6) v = __dadd_rn(v, dt[tau]);                    // :92-94 (dt is 0 at g == nb-1)
-                G[k] = v;
-            }
-#pragma unroll
-            for (int tau = 0; tau < 7; ++tau) dtprev[tau] = -dt[tau];
-            // rotate the block accumulators: acc[k] holds S7(h = g-k) through cell k
-            const double done = __dadd_rn(acc[5], G[6]);
-#pragma unroll
-            for (int k = 5; k >= 1; --k) acc[k] = __dadd_rn(acc[k - 1], G[k]);
-            acc[0] = G[0];
-            // S7(h = g-6) is complete
-            {
-                const int h = g - 6;
-#pragma unroll
-                for (int m = 0; m < 3; ++m) {
-                    const int u = h + 10 - m * kSyncOffset;
-                    if (u >= 0 && u < nu) sc[u * kSyncThreads + tid] = __dadd_rn(sc[u * kSyncThreads + tid], done);
-                }
-            }
-        }
-        // flush partial blocks that run past the last symbol: h = nb-6 .. nb-1 (acc[5] .. acc[0])
-#pragma unroll
-        for (int k = 5; k >= 0; --k) {
-            const int h = nb - 1 - k;
-#pragma unroll
-            for (int m = 0; m < 3; ++m) {
-                const int u = h + 10 - m * kSyncOffset;
-                if (u >= 0 && u < nu) sc[u * kSyncThreads + tid] = __dadd_rn(sc[u * kSyncThreads + tid], acc[k]);
-            }
-        }
-        // normalise and store: score / num_comparisons, -inf when no comparison or non-finite (:97-100)
-        double *out = a.scores + slot * (int64_t)(nu * s) * a.nf + f;
-        for (int u = 0; u < nu; ++u) {
-            const int n = ncmp[u];
-            double v = sc[u * kSyncThreads + tid];
-            if (n == 0 || !isfinite(v)) v = -INFINITY;
-            else v = __ddiv_rn(v, (double)n);
-            out[(int64_t)(rho + s * u) * a.nf] = v;
-        }
+    for (int k = 5; k >= 0; --k) sync_scatter(scp, nb - 1 - k, nu, acc[k]);
+    // normalise and store: score / num_comparisons, -inf when no comparison or non-finite (ft8_decode.py:97-100)
+    double *out = a.scores + slot * (int64_t)(nu * s) * a.nf + (int64_t)rho * a.nf + f;
+    const int64_t outstep = (int64_t)s * a.nf;
+    for (int u = 0; u < nu; ++u) {
+        const int n = ncmp[u];
+        double v = scp[u * kSyncThreads];
+        v = (n == 0 || !isfinite(v)) ? -INFINITY : __ddiv_rn(v, (double)n);
+        out[u * outstep] = v;
     }
 }
 
@@ -328,7 +379,8 @@ int sync_scores(const double *mag, int64_t n_slots, int T, int F, int s, int b, 
     SyncArgs a;
     a.mag = mag; a.scores = scores; a.T = T; a.F = F; a.s = s; a.b = b;
     a.nb = T / s; a.nu = nt / s; a.nf = nf;
-    const size_t smem = sizeof(double) * (size_t)a.nu * kSyncThreads + sizeof(int) * (size_t)a.nu;
+    const size_t smem = sizeof(double) * ((size_t)a.nu * kSyncThreads + (size_t)(kSyncThreads / 32) * kSyncStages * (32 + 7 * b)) +
+                        sizeof(int) * (size_t)a.nu;
     int dev = 0, max_smem = 0;
     FT8B_CUDA_TRY(cudaGetDevice(&dev));
     FT8B_CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
@@ -340,9 +392,20 @@ int sync_scores(const double *mag, int64_t n_slots, int T, int F, int s, int b, 
         set_error("ft8b_sync_scores: steps_per_symbol and slots per call must be <= 65535");
         return FT8B_ERR_UNSUPPORTED;
     }
-    FT8B_CUDA_TRY(cudaFuncSetAttribute(sync_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
     dim3 grid((nf + kSyncThreads - 1) / kSyncThreads, s, (unsigned)n_slots);
-    sync_scores_kernel<<<grid, kSyncThreads, smem, stream>>>(a);
+#define FT8B_SYNC_LAUNCH(BB)                                                                                         \
+    do {                                                                                                             \
+        FT8B_CUDA_TRY(cudaFuncSetAttribute(sync_scores_kernel<BB>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                           (int)max_smem));                                                          \
+        sync_scores_kernel<BB><<<grid, kSyncThreads, smem, stream>>>(a);                                             \
+    } while (0)
+    switch (b) {           // freq_osr as a compile-time constant turns the 8 tone offsets into immediates
+        case 1: FT8B_SYNC_LAUNCH(1); break;
+        case 2: FT8B_SYNC_LAUNCH(2); break;
+        case 4: FT8B_SYNC_LAUNCH(4); break;
+        default: FT8B_SYNC_LAUNCH(0); break;
+    }
+#undef FT8B_SYNC_LAUNCH
     FT8B_LAUNCH_CHECK("sync_scores_kernel");
     return 0;
 }

@@ -84,9 +84,13 @@ def test_stft_fast_path_equals_generic_path(monkeypatch):
 
 
 def test_stft_signal_floor():
-    """All-zero audio hits the 1e-12 floor exactly: 10*log10(1e-12) (spectrogram_analyse.py:60)."""
+    """All-zero audio sits on the 1e-12 floor, 10*log10(1e-12) (spectrogram_analyse.py:60), and the map is
+    exactly constant, so every sync score of digital silence is exactly 0 as in the reference."""
     got = gpu_mag(np.zeros(20000), 12000, 2, 2)
-    assert torch.all(got == 10.0 * np.log10(1e-12))
+    assert (got - 10.0 * np.log10(1e-12)).abs().max().item() < 1e-12
+    assert torch.all(got == got.flatten()[0])
+    scores, _ = engine.sync_scores(gpu_mag(np.zeros(180000), 12000, 2, 2), 2, 2)
+    assert torch.all(scores == 0.0)
 
 
 def test_calculate_spectrogram_dropin(c1_slot):
