@@ -350,6 +350,15 @@ static int get_plan(int nperseg, int nfft, const StftPlan **out) {
         FT8B_CUDA_TRY(cudaMalloc(&p.tw3, sizeof(double2) * t3.size()));
         FT8B_CUDA_TRY(cudaMemcpy(p.tw2, t2.data(), sizeof(double2) * t2.size(), cudaMemcpyHostToDevice));
         FT8B_CUDA_TRY(cudaMemcpy(p.tw3, t3.data(), sizeof(double2) * t3.size(), cudaMemcpyHostToDevice));
+        // 4 resident CTAs need 4 x 33 KB of shared memory; ask for a ~132 KB carve-out so the rest of the 256 KB
+        // stays L1 and the 80 KB of window/twiddle tables remain cache resident.
+        static const int carve = [] { const char *e = getenv("FT8B_STFT_CARVEOUT"); return e ? atoi(e) : 60; }();
+        if (carve >= 0) {
+            cudaFuncSetAttribute(stft1920_kernel<float, 4, true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+            cudaFuncSetAttribute(stft1920_kernel<float, 4, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+            cudaFuncSetAttribute(stft1920_kernel<double, 4, true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+            cudaFuncSetAttribute(stft1920_kernel<double, 4, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        }
         p.fast = 1;
     }
     auto ins = g_plans.emplace(key, p);

@@ -156,11 +156,9 @@ __device__ __forceinline__ void bf8(double2 (&a)[8]) {
 // slow-path branch per element).  v = 2^e * m, m in [1,2); i = top 7 mantissa bits; r = m * (1/c_i) - 1 with
 // |r| <= 2^-8; 10*log10(v) = e*10*log10(2) + 10*log10(c_i) + (10/ln 10) * (r - r^2/2 + ... + r^7/7).
 // Max error 2.4e-14 dB against extended precision over [1e-12, 1e4] (np.log10 itself: 1.6e-14 dB).
-__device__ __noinline__ double slow_db(double v) { return 10.0 * log10(v); }
-
 __device__ __forceinline__ double fast_db(double v, const double2 *__restrict__ tab) {
+    // branch-free: inf / NaN inputs (never produced by finite audio) are patched in at the end with selects
     const long long bits = __double_as_longlong(v);
-    if (bits >= 0x7ff0000000000000LL || bits <= 0) return slow_db(v);          // inf / NaN / non-positive: libdevice path
     const int e = (int)(bits >> 52) - 1023;
     const int i = (int)(bits >> 45) & 127;
     const double m = __longlong_as_double((bits & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);
@@ -173,11 +171,14 @@ __device__ __forceinline__ double fast_db(double v, const double2 *__restrict__ 
     p = fma(p, r, kK[20]);                          //  (10/ln10)/3
     p = fma(p, r, kK[21]);                          // -(10/ln10)/2
     p = fma(p, r, kK[22]);                          //  (10/ln10)
-    return fma(r, p, fma((double)e, kK[23], t.y));
+    const double res = fma(r, p, fma((double)e, kK[23], t.y));
+    return (bits >= 0x7ff0000000000000LL) ? v + v : res;     // +inf -> +inf, NaN -> NaN (as 10*log10 would)
 }
 
 // Untangle the pair (Z[k], Z[M-k]) of the packed transform and emit dB for bins k and M-k
 // (spectrogram_analyse.py:59-60: 10*log10(1e-12 + |S|), S = |X|^2 / (sum w)^2).
+// FULL: the caller guarantees 1 <= k <= 1919 and that bins 0..1919 are all stored (no range checks).
+template <bool FULL>
 __device__ __forceinline__ void emit_pair(double2 z, double2 zr, int k, const Stft1920Args &a, double *out,
                                           const double2 *__restrict__ tab) {
     const double2 zc = make_double2(zr.x, -zr.y);
@@ -186,9 +187,15 @@ __device__ __forceinline__ void emit_pair(double2 z, double2 zr, int k, const St
     const int k2 = kM1920 - k;
     const double re1 = e.x + 0.5 * p.y, im1 = e.y - 0.5 * p.x;
     const double re2 = e.x - 0.5 * p.y, im2 = e.y + 0.5 * p.x;
-    if (k >= a.bin_lo && k < a.bin_hi) out[k - a.bin_lo] = fast_db(kK[24] + (re1 * re1 + im1 * im1) * a.scale, tab);
-    if (k2 != k && k2 >= a.bin_lo && k2 < a.bin_hi)
-        out[k2 - a.bin_lo] = fast_db(kK[24] + (re2 * re2 + im2 * im2) * a.scale, tab);
+    const double d1 = fast_db(kK[24] + (re1 * re1 + im1 * im1) * a.scale, tab);
+    const double d2 = fast_db(kK[24] + (re2 * re2 + im2 * im2) * a.scale, tab);
+    if (FULL) {
+        out[k] = d1;
+        out[k2] = d2;
+    } else {
+        if (k >= a.bin_lo && k < a.bin_hi) out[k - a.bin_lo] = d1;
+        if (k2 != k && k2 >= a.bin_lo && k2 < a.bin_hi) out[k2 - a.bin_lo] = d2;
+    }
 }
 
 }  // namespace f1920
@@ -212,6 +219,7 @@ __global__ void __launch_bounds__(kStft1920Threads, MB) stft1920_kernel(const St
     __syncthreads();
     const int64_t n_items = a.n_slots * a.frames_out;
     const int Fout = a.bin_hi - a.bin_lo;
+    const bool full = (a.bin_lo == 0) && (a.bin_hi >= kM1920);   // bins 0..1919 all stored: no per-bin range checks
     for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int64_t slot = item / a.frames_out;
         const int64_t fr = item - slot * a.frames_out;
@@ -277,8 +285,13 @@ __global__ void __launch_bounds__(kStft1920Threads, MB) stft1920_kernel(const St
             bf8(u1);
             bf8(u2);
             if (tid < 120) {
+                if (full) {
 #pragma unroll
-                for (int t = 0; t < 8; ++t) emit_pair(u1[t], u2[7 - t], j1 + 240 * t, a, out, logtab);
+                    for (int t = 0; t < 8; ++t) emit_pair<true>(u1[t], u2[7 - t], j1 + 240 * t, a, out, logtab);
+                } else {
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) emit_pair<false>(u1[t], u2[7 - t], j1 + 240 * t, a, out, logtab);
+                }
             } else {
 #pragma unroll
                 for (int t = 0; t < 8; ++t) { sp[t] = u1[t]; sp[8 + t] = u2[t]; }
@@ -292,7 +305,7 @@ __global__ void __launch_bounds__(kStft1920Threads, MB) stft1920_kernel(const St
                     const int t = (q < 5) ? q : q - 5;
                     const double2 z = (q < 5) ? sp[t] : sp[8 + t];
                     const double2 zr = (q < 5) ? sp[(8 - t) & 7] : sp[15 - t];
-                    emit_pair(z, zr, (q < 5) ? 240 * t : 120 + 240 * t, a, out, logtab);
+                    emit_pair<false>(z, zr, (q < 5) ? 240 * t : 120 + 240 * t, a, out, logtab);
                 }
             }
         }

@@ -96,18 +96,6 @@ __device__ __forceinline__ void sync_scatter(double *scp, int h, int nu, double 
 
 constexpr int kSyncStages = 5;   // spectrogram columns staged per warp: 2 in use + 3 in flight
 
-// Stage column `g` (clamped to the last one) of this warp's frequency strip into its ring slot with cp.async:
-// `w` values starting at bin f0, 8 bytes each, one or two per lane.  Every lane commits exactly one group per call.
-__device__ __forceinline__ void sync_stage_column(double *ring, int ring_w, const double *col0, int64_t rowstep, int g,
-                                                  int last, int w, int f_room, int lane) {
-    const int gc = g < last ? g : last;
-    const double *src = col0 + rowstep * gc;
-    double *dst = ring + (g % kSyncStages) * ring_w;
-    for (int it = 0, i = lane; it < (w + 31) / 32; ++it, i += 32)
-        if (i < w && i < f_room) __pipeline_memcpy_async(dst + i, src + i, 8);
-    __pipeline_commit();
-}
-
 template <int B>
 __global__ void __launch_bounds__(kSyncThreads) sync_scores_kernel(const SyncArgs a) {
     extern __shared__ double sc[];   // [nu][kSyncThreads] score sums | ring[4 warps][kSyncStages][ring_w] | int ncmp[nu]
@@ -138,30 +126,63 @@ __global__ void __launch_bounds__(kSyncThreads) sync_scores_kernel(const SyncArg
     for (int k = 0; k < 7; ++k) dtprev[k] = 0.0;
 #pragma unroll
     for (int k = 0; k < 6; ++k) acc[k] = 0.0;
-    // prologue: columns 0 .. kSyncStages-2 in flight
+    // All addressing below is incremental (no per-step multiplies / modulo): staging source and ring slots advance
+    // by constant strides and wrap with one compare.
+    double *const ring_lane = ring + lane;
+    double *const ring_end = ring_lane + kSyncStages * ring_w;
+    const double *src = col0 + lane;                     // column min(sg, last), this lane's first bin
+    double *dst = ring_lane;                             // slot sg % kSyncStages
+    int sg = 0;                                          // next column to stage
+    const bool p0 = lane < f_room;
+    const bool p1 = (lane + 32 < ring_w) && (lane + 32 < f_room);
+    auto stage = [&]() {                                 // one commit group per call on every lane
+        if (B > 0) {                                     // ring_w <= 60: at most two 8-byte copies per lane
+            if (p0) __pipeline_memcpy_async(dst, src, 8);
+            if (p1) __pipeline_memcpy_async(dst + 32, src + 32, 8);
+        } else {
+            for (int it = 0, i = lane; it < (ring_w + 31) / 32; ++it, i += 32)
+                if (i < ring_w && i < f_room) __pipeline_memcpy_async(dst + (i - lane), src + (i - lane), 8);
+        }
+        __pipeline_commit();
+        if (sg < last) src += rowstep;
+        ++sg;
+        dst += ring_w;
+        if (dst == ring_end) dst = ring_lane;
+    };
+    // prologue: columns 0 .. kSyncStages-2 in flight, column 0 landed
 #pragma unroll
-    for (int g = 0; g < kSyncStages - 1; ++g) sync_stage_column(ring, ring_w, col0, rowstep, g, last, ring_w, f_room, lane);
-    __pipeline_wait_prior(kSyncStages - 2);              // column 0 has landed
+    for (int g = 0; g < kSyncStages - 1; ++g) stage();
+    __pipeline_wait_prior(kSyncStages - 2);
     __syncwarp();
     if (active) {
 #pragma unroll
-        for (int tau = 0; tau < 8; ++tau) ca[tau] = ring[lane + tau * bo];
+        for (int tau = 0; tau < 8; ++tau) ca[tau] = ring_lane[tau * bo];
     }
+    const double *rd = ring_lane + ring_w;               // slot of column g+1
+    double *sp = scp + 4 * kSyncThreads;                 // &score[u = g+4] : target of block m = 0 for h = g-6
     // Steady state, unrolled by two so `cur`/`nxt` swap by renaming.  At step g: stage column g+4, wait until
-    // column g+1 has landed (3 younger groups may still be in flight), read it, do the arithmetic.
+    // column g+1 has landed (3 younger groups may still be in flight), read it, do the arithmetic, then add the
+    // finished block sum S7(h = g-6) into score[u] for u = h+10, h-26, h-62 (m = 0, 1, 2).
 #define FT8B_SYNC_STEP(CUR, NXT, G, HASNEXT)                                                                  \
     do {                                                                                                      \
         __syncwarp();                                                                                         \
-        sync_stage_column(ring, ring_w, col0, rowstep, (G) + kSyncStages - 1, last, ring_w, f_room, lane);    \
+        stage();                                                                                              \
         __pipeline_wait_prior(kSyncStages - 2);                                                               \
         __syncwarp();                                                                                         \
         if (active) {                                                                                         \
             if (HASNEXT) {                                                                                    \
-                const double *rp_ = ring + (((G) + 1) % kSyncStages) * ring_w + lane;                         \
-                _Pragma("unroll") for (int tau = 0; tau < 8; ++tau) NXT[tau] = rp_[tau * bo];                 \
+                _Pragma("unroll") for (int tau = 0; tau < 8; ++tau) NXT[tau] = rd[tau * bo];                  \
             }                                                                                                 \
-            sync_scatter(scp, (G)-6, nu, sync_step<HASNEXT>(CUR, NXT, dtprev, acc));                          \
+            const double done_ = sync_step<HASNEXT>(CUR, NXT, dtprev, acc);                                   \
+            if ((unsigned)((G) + 4) < (unsigned)nu) sp[0] = __dadd_rn(sp[0], done_);                          \
+            if ((unsigned)((G)-32) < (unsigned)nu)                                                            \
+                sp[-kSyncOffset * kSyncThreads] = __dadd_rn(sp[-kSyncOffset * kSyncThreads], done_);          \
+            if ((unsigned)((G)-68) < (unsigned)nu)                                                            \
+                sp[-2 * kSyncOffset * kSyncThreads] = __dadd_rn(sp[-2 * kSyncOffset * kSyncThreads], done_);  \
         }                                                                                                     \
+        rd += ring_w;                                                                                         \
+        if (rd == ring_end) rd = ring_lane;                                                                   \
+        sp += kSyncThreads;                                                                                   \
     } while (0)
     int g = 0;
     for (; g + 2 <= last; g += 2) {
