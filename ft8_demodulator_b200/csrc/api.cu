@@ -224,7 +224,7 @@ int ft8b_decode_slots(const void *wave, int wave_dtype, int64_t n_slots, int64_t
     cudaStream_t stream = (cudaStream_t)stream_;
     if (!p || !wave || !workspace || !cand_time || !cand_freq || !cand_score || !n_cand || !ok || !ldpc_errors || !payload)
         FT8B_ARG_FAIL("ft8b_decode_slots: null pointer");
-    if (wave_dtype != FT8B_DTYPE_F32 && wave_dtype != FT8B_DTYPE_F64) FT8B_ARG_FAIL("ft8b_decode_slots: bad dtype");
+    if (wave_dtype != FT8B_DTYPE_F32 && wave_dtype != FT8B_DTYPE_F64 && wave_dtype != FT8B_DTYPE_I16) FT8B_ARG_FAIL("ft8b_decode_slots: bad dtype");
     if (p->max_candidates < 0 || p->max_candidates > FT8B_MAX_CANDIDATES) {
         set_error("ft8b_decode_slots: max_candidates=%d outside [0,%d]", p->max_candidates, FT8B_MAX_CANDIDATES);
         return FT8B_ERR_UNSUPPORTED;
@@ -234,7 +234,7 @@ int ft8b_decode_slots(const void *wave, int wave_dtype, int64_t n_slots, int64_t
     if (rc) return rc;
     if (n_slots <= 0) return 0;
     const int K = p->max_candidates;
-    const size_t elt = wave_dtype == FT8B_DTYPE_F32 ? 4 : 8;
+    const size_t elt = wave_dtype == FT8B_DTYPE_F32 ? 4 : (wave_dtype == FT8B_DTYPE_I16 ? 2 : 8);
     const int64_t per_slot = 8 * (g.mag_elems + g.score_elems);
     if (g.T <= 0 || g.F <= 0 || g.score_elems == 0 || K == 0) {
         // nothing to search: the reference returns an empty list

@@ -189,6 +189,9 @@ __device__ __noinline__ void fft_pass_prime(double2 *s, int M, int Ns, int p, co
 
 template <typename T>
 __device__ __forceinline__ double load_sample(const T *x, int i) { return (double)x[i]; }
+// int16 PCM: float32(x) / 32767.0f in float32, exactly what from_wave.py:62-66 computes on the host
+template <>
+__device__ __forceinline__ double load_sample<short>(const short *x, int i) { return (double)__fdiv_rn((float)x[i], 32767.0f); }
 
 // BOUND = the largest block size the instantiation may be launched with (register budget).
 template <typename WaveT, int BOUND>
@@ -327,6 +330,8 @@ static int get_plan(int nperseg, int nfft, const StftPlan **out) {
     FT8B_CUDA_TRY(cudaFuncSetAttribute(stft_db_kernel<double, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     FT8B_CUDA_TRY(cudaFuncSetAttribute(stft_db_kernel<float, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     FT8B_CUDA_TRY(cudaFuncSetAttribute(stft_db_kernel<double, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    FT8B_CUDA_TRY(cudaFuncSetAttribute(stft_db_kernel<short, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    FT8B_CUDA_TRY(cudaFuncSetAttribute(stft_db_kernel<short, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     if (nperseg == 1920 && nfft == 3840) {
         std::vector<double2> t2(16 * 15), t3(8 * 240);
         for (int t = 0; t < 16; ++t)
@@ -350,15 +355,20 @@ static int get_plan(int nperseg, int nfft, const StftPlan **out) {
         FT8B_CUDA_TRY(cudaMalloc(&p.tw3, sizeof(double2) * t3.size()));
         FT8B_CUDA_TRY(cudaMemcpy(p.tw2, t2.data(), sizeof(double2) * t2.size(), cudaMemcpyHostToDevice));
         FT8B_CUDA_TRY(cudaMemcpy(p.tw3, t3.data(), sizeof(double2) * t3.size(), cudaMemcpyHostToDevice));
-        // 4 resident CTAs need 4 x 33 KB of shared memory; ask for a ~132 KB carve-out so the rest of the 256 KB
-        // stays L1 and the 80 KB of window/twiddle tables remain cache resident.
-        static const int carve = [] { const char *e = getenv("FT8B_STFT_CARVEOUT"); return e ? atoi(e) : 60; }();
-        if (carve >= 0) {
-            cudaFuncSetAttribute(stft1920_kernel<float, 4, true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-            cudaFuncSetAttribute(stft1920_kernel<float, 4, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-            cudaFuncSetAttribute(stft1920_kernel<double, 4, true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-            cudaFuncSetAttribute(stft1920_kernel<double, 4, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-        }
+        static const int carve = [] { const char *e = getenv("FT8B_STFT_CARVEOUT"); return e ? atoi(e) : -1; }();
+#define FT8B_STFT1920_ATTR(T, MB, V)                                                                                   \
+    do {                                                                                                               \
+        FT8B_CUDA_TRY(cudaFuncSetAttribute(stft1920_kernel<T, MB, V>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                           (int)stft1920_smem_bytes<T, V>()));                                         \
+        if (carve >= 0)                                                                                                \
+            cudaFuncSetAttribute(stft1920_kernel<T, MB, V>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);    \
+    } while (0)
+        FT8B_STFT1920_ATTR(float, 4, true);  FT8B_STFT1920_ATTR(float, 4, false);
+        FT8B_STFT1920_ATTR(float, 5, true);  FT8B_STFT1920_ATTR(float, 5, false);
+        FT8B_STFT1920_ATTR(double, 4, true); FT8B_STFT1920_ATTR(double, 4, false);
+        FT8B_STFT1920_ATTR(double, 5, true); FT8B_STFT1920_ATTR(double, 5, false);
+        FT8B_STFT1920_ATTR(short, 4, true);  FT8B_STFT1920_ATTR(short, 4, false);
+#undef FT8B_STFT1920_ATTR
         p.fast = 1;
     }
     auto ins = g_plans.emplace(key, p);
@@ -384,7 +394,7 @@ int stft_db(const void *wave, int wave_dtype, int64_t n_slots, int64_t n_samples
             int hop, int nfft, int bin_lo, int bin_hi, int64_t frame_lo, int64_t frame_hi, double *mag,
             cudaStream_t stream) {
     if (!wave || !mag) FT8B_ARG_FAIL("ft8b_stft_db: null pointer");
-    if (wave_dtype != FT8B_DTYPE_F32 && wave_dtype != FT8B_DTYPE_F64) FT8B_ARG_FAIL("ft8b_stft_db: bad dtype %d", wave_dtype);
+    if (wave_dtype != FT8B_DTYPE_F32 && wave_dtype != FT8B_DTYPE_F64 && wave_dtype != FT8B_DTYPE_I16) FT8B_ARG_FAIL("ft8b_stft_db: bad dtype %d", wave_dtype);
     if (nperseg < 1 || hop < 1 || nfft < nperseg) FT8B_ARG_FAIL("ft8b_stft_db: need 1 <= nperseg <= nfft, hop >= 1");
     if (n_slots < 0 || slot_stride < n_samples) FT8B_ARG_FAIL("ft8b_stft_db: bad batch geometry");
     const int64_t T = ft8b_num_frames(n_samples, nperseg, hop);
@@ -405,15 +415,18 @@ int stft_db(const void *wave, int wave_dtype, int64_t n_slots, int64_t n_samples
         int64_t g1920 = items < 148 * 32 ? items : 148 * 32;
         static const int mb = [] { const char *e = getenv("FT8B_STFT_MINBLOCKS"); return e ? atoi(e) : 4; }();
         // vector loads of sample pairs need every frame start to be 2-element aligned
-        const size_t pair_bytes = wave_dtype == FT8B_DTYPE_F32 ? 8 : 16;
+        // the staged path copies sample pairs with cp.async: every frame start must be pair aligned
+        const size_t pair_bytes = wave_dtype == FT8B_DTYPE_F32 ? 8 : (wave_dtype == FT8B_DTYPE_I16 ? 4 : 16);
         const bool vec = (reinterpret_cast<uintptr_t>(wave) % pair_bytes == 0) && (slot_stride % 2 == 0) && (hop % 2 == 0);
 #define FT8B_STFT1920(T, MB)                                                                              \
     do {                                                                                                  \
-        if (vec) stft1920_kernel<T, MB, true><<<(unsigned)g1920, kStft1920Threads, 0, stream>>>(f);      \
-        else stft1920_kernel<T, MB, false><<<(unsigned)g1920, kStft1920Threads, 0, stream>>>(f);         \
+        if (vec) stft1920_kernel<T, MB, true><<<(unsigned)g1920, kStft1920Threads, stft1920_smem_bytes<T, true>(), stream>>>(f);   \
+        else stft1920_kernel<T, MB, false><<<(unsigned)g1920, kStft1920Threads, stft1920_smem_bytes<T, false>(), stream>>>(f);     \
     } while (0)
         if (wave_dtype == FT8B_DTYPE_F32) {
             if (mb == 5) FT8B_STFT1920(float, 5); else FT8B_STFT1920(float, 4);
+        } else if (wave_dtype == FT8B_DTYPE_I16) {
+            FT8B_STFT1920(short, 4);
         } else {
             if (mb == 5) FT8B_STFT1920(double, 5); else FT8B_STFT1920(double, 4);
         }
@@ -434,7 +447,10 @@ int stft_db(const void *wave, int wave_dtype, int64_t n_slots, int64_t n_samples
     const int64_t cap = 148 * 64;  // persistent-ish: many CTAs per SM, grid-stride over frames
     if (grid > cap) grid = cap;
     const bool small = plan->nthreads <= 256;
-    if (wave_dtype == FT8B_DTYPE_F32) {
+    if (wave_dtype == FT8B_DTYPE_I16) {
+        if (small) stft_db_kernel<short, 256><<<(unsigned)grid, plan->nthreads, plan->smem, stream>>>(a);
+        else stft_db_kernel<short, 1024><<<(unsigned)grid, plan->nthreads, plan->smem, stream>>>(a);
+    } else if (wave_dtype == FT8B_DTYPE_F32) {
         if (small) stft_db_kernel<float, 256><<<(unsigned)grid, plan->nthreads, plan->smem, stream>>>(a);
         else stft_db_kernel<float, 1024><<<(unsigned)grid, plan->nthreads, plan->smem, stream>>>(a);
     } else {

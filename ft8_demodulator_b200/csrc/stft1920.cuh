@@ -11,6 +11,8 @@
 //                           are applied there and the dB values go straight to HBM.
 // Shared-memory traffic per frame is 4 x 30 KB (one write + read per pass boundary), 4 block barriers.
 #pragma once
+#include <cuda_pipeline.h>
+
 #include "common.cuh"
 
 namespace ft8b {
@@ -172,59 +174,99 @@ __device__ __forceinline__ double fast_db(double v, const double2 *__restrict__ 
     p = fma(p, r, kK[21]);                          // -(10/ln10)/2
     p = fma(p, r, kK[22]);                          //  (10/ln10)
     const double res = fma(r, p, fma((double)e, kK[23], t.y));
-    return (bits >= 0x7ff0000000000000LL) ? v + v : res;     // +inf -> +inf, NaN -> NaN (as 10*log10 would)
+    return (__double2hiint(v) >= 0x7ff00000) ? v + v : res;  // +inf -> +inf, NaN -> NaN (as 10*log10 would); v > 0
 }
 
 // Untangle the pair (Z[k], Z[M-k]) of the packed transform and emit dB for bins k and M-k
 // (spectrogram_analyse.py:59-60: 10*log10(1e-12 + |S|), S = |X|^2 / (sum w)^2).
-// FULL: the caller guarantees 1 <= k <= 1919 and that bins 0..1919 are all stored (no range checks).
-template <bool FULL>
-__device__ __forceinline__ void emit_pair(double2 z, double2 zr, int k, const Stft1920Args &a, double *out,
-                                          const double2 *__restrict__ tab) {
+// Untangle the pair (Z[k], Z[M-k]) of the packed transform into dB for bins k and M-k
+// (spectrogram_analyse.py:59-60: 10*log10(1e-12 + |S|), S = |X|^2 / (sum w)^2).
+__device__ __forceinline__ void untangle_pair(double2 z, double2 zr, double2 w, double scale, const double2 *__restrict__ tab,
+                                              double &d1, double &d2) {
     const double2 zc = make_double2(zr.x, -zr.y);
     const double2 e = make_double2(0.5 * (z.x + zc.x), 0.5 * (z.y + zc.y));
-    const double2 p = cmul(__ldg(&a.twpost[k]), csub(z, zc));
-    const int k2 = kM1920 - k;
+    const double2 p = cmul(w, csub(z, zc));
     const double re1 = e.x + 0.5 * p.y, im1 = e.y - 0.5 * p.x;
     const double re2 = e.x - 0.5 * p.y, im2 = e.y + 0.5 * p.x;
-    const double d1 = fast_db(kK[24] + (re1 * re1 + im1 * im1) * a.scale, tab);
-    const double d2 = fast_db(kK[24] + (re2 * re2 + im2 * im2) * a.scale, tab);
-    if (FULL) {
-        out[k] = d1;
-        out[k2] = d2;
-    } else {
-        if (k >= a.bin_lo && k < a.bin_hi) out[k - a.bin_lo] = d1;
-        if (k2 != k && k2 >= a.bin_lo && k2 < a.bin_hi) out[k2 - a.bin_lo] = d2;
-    }
+    d1 = fast_db(kK[24] + (re1 * re1 + im1 * im1) * scale, tab);
+    d2 = fast_db(kK[24] + (re2 * re2 + im2 * im2) * scale, tab);
+}
+
+// general form with band crop: stores bins k and M-k when they fall inside [bin_lo, bin_hi)
+__device__ __forceinline__ void emit_pair(double2 z, double2 zr, int k, const Stft1920Args &a, double *out,
+                                          const double2 *__restrict__ tab) {
+    double d1, d2;
+    untangle_pair(z, zr, __ldg(&a.twpost[k]), a.scale, tab, d1, d2);
+    const int k2 = kM1920 - k;
+    if (k >= a.bin_lo && k < a.bin_hi) out[k - a.bin_lo] = d1;
+    if (k2 != k && k2 >= a.bin_lo && k2 < a.bin_hi) out[k2 - a.bin_lo] = d2;
 }
 
 }  // namespace f1920
 
 // samples 2n, 2n+1 as one vector load (the caller guarantees 8/16-byte alignment when VEC is set)
 __device__ __forceinline__ double2 load_pair(const float *x, int n) {
-    const float2 v = __ldg(reinterpret_cast<const float2 *>(x) + n);
+    const float2 v = reinterpret_cast<const float2 *>(x)[n];
     return make_double2((double)v.x, (double)v.y);
 }
-__device__ __forceinline__ double2 load_pair(const double *x, int n) { return __ldg(reinterpret_cast<const double2 *>(x) + n); }
+__device__ __forceinline__ double2 load_pair(const double *x, int n) { return reinterpret_cast<const double2 *>(x)[n]; }
+__device__ __forceinline__ double from_pcm16(short v) { return (double)__fdiv_rn((float)v, 32767.0f); }   // from_wave.py:62-66
+__device__ __forceinline__ double2 load_pair(const short *x, int n) {
+    const short2 v = reinterpret_cast<const short2 *>(x)[n];
+    return make_double2(from_pcm16(v.x), from_pcm16(v.y));
+}
+__device__ __forceinline__ double to_sample(float v) { return (double)v; }
+__device__ __forceinline__ double to_sample(double v) { return v; }
+__device__ __forceinline__ double to_sample(short v) { return from_pcm16(v); }
+
+template <typename WaveT, bool VEC>
+constexpr size_t stft1920_smem_bytes() {
+    return sizeof(double2) * (kM1920 + 16 + 128 + 16 * 15) + (VEC ? sizeof(WaveT) * kM1920 : 16);
+}
 
 // MB = CTAs per SM the register allocation must allow (4: 128 regs, 5: 96 regs, 6: 80 regs)
 template <typename WaveT, int MB, bool VEC>
 __global__ void __launch_bounds__(kStft1920Threads, MB) stft1920_kernel(const Stft1920Args a) {
     using namespace f1920;
-    __shared__ double2 s[kM1920];
-    __shared__ double2 sp[16];
-    __shared__ double2 logtab[128];
+    extern __shared__ __align__(16) unsigned char smem1920[];     // stft1920_smem_bytes<WaveT, VEC>()
+    double2 *s = reinterpret_cast<double2 *>(smem1920);           // [1920] the frame being transformed
+    double2 *sp = s + kM1920;                                     // [16]   self-paired butterfly outputs
+    double2 *logtab = sp + 16;                                    // [128]
+    double2 *tw2s = logtab + 128;                                 // [16*15]
+    // VEC path: the next frame's 1920 samples are staged here with cp.async while this frame is transformed
+    WaveT *xs = reinterpret_cast<WaveT *>(tw2s + 16 * 15);        // [1920]
     const int tid = threadIdx.x;
     logtab[tid] = __ldg(&a.logtab[tid]);
-    __syncthreads();
+    for (int i = tid; i < 16 * 15; i += kStft1920Threads) tw2s[i] = __ldg(&a.tw2[i]);
     const int64_t n_items = a.n_slots * a.frames_out;
     const int Fout = a.bin_hi - a.bin_lo;
     const bool full = (a.bin_lo == 0) && (a.bin_hi >= kM1920);   // bins 0..1919 all stored: no per-bin range checks
+    auto frame_audio = [&](int64_t it) -> const WaveT * {
+        const int64_t sl = it / a.frames_out;
+        return reinterpret_cast<const WaveT *>(a.wave) + sl * a.slot_stride + (it - sl * a.frames_out + a.frame_lo) * a.hop;
+    };
+    // Each thread copies exactly the sample pairs it will consume in P1 (n = tid + 128 t), so waiting on its own
+    // cp.async groups is enough - no block barrier guards the staging buffer.
+    auto stage_audio = [&](int64_t it) {
+        if (VEC && it < n_items) {
+            constexpr int kPair = 2 * (int)sizeof(WaveT);
+            const char *src = reinterpret_cast<const char *>(frame_audio(it));
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const int n = tid + 128 * t;
+                if (t < 7 || tid < 64) __pipeline_memcpy_async(reinterpret_cast<char *>(xs) + kPair * n, src + kPair * n, kPair);
+            }
+        }
+        __pipeline_commit();
+    };
+    stage_audio(blockIdx.x);
+    __syncthreads();
     for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int64_t slot = item / a.frames_out;
         const int64_t fr = item - slot * a.frames_out;
-        const WaveT *x = reinterpret_cast<const WaveT *>(a.wave) + slot * a.slot_stride + (fr + a.frame_lo) * a.hop;
+        const WaveT *x = VEC ? xs : frame_audio(item);
         double *out = a.mag + (slot * a.frames_out + fr) * (int64_t)Fout;
+        if (VEC) __pipeline_wait_prior(0);     // this thread's pairs of this frame have landed
         // ---------------- P1: radix 15, inputs z[j + 128 t] = (w x)[2n] + i (w x)[2n+1], zero for n >= 960
         {
             double2 u[15];
@@ -237,7 +279,7 @@ __global__ void __launch_bounds__(kStft1920Threads, MB) stft1920_kernel(const St
                         const auto xv = load_pair(x, n);
                         u[t] = make_double2(w.x * xv.x, w.y * xv.y);
                     } else {
-                        u[t] = make_double2(w.x * (double)x[2 * n], w.y * (double)x[2 * n + 1]);
+                        u[t] = make_double2(w.x * to_sample(x[2 * n]), w.y * to_sample(x[2 * n + 1]));
                     }
                 } else {
                     u[t] = make_double2(0.0, 0.0);
@@ -246,9 +288,14 @@ __global__ void __launch_bounds__(kStft1920Threads, MB) stft1920_kernel(const St
 #pragma unroll
             for (int t = 8; t < 15; ++t) u[t] = make_double2(0.0, 0.0);
             bf15(u);
+            // Barrier here rather than at the end of the loop: warps that finished the previous frame's P3 early
+            // have already loaded and transformed their share of this frame; `s` (still read by slower warps in
+            // P3) and the audio staging buffer are only touched after everybody has arrived.
+            __syncthreads();
 #pragma unroll
             for (int pos = 0; pos < 15; ++pos) s[tid * 15 + out15(pos)] = u[pos];
         }
+        stage_audio(item + gridDim.x);         // lands during P2/P3
         __syncthreads();
         // ---------------- P2: radix 16, Ns = 15
         {
@@ -258,7 +305,7 @@ __global__ void __launch_bounds__(kStft1920Threads, MB) stft1920_kernel(const St
 #pragma unroll
                 for (int t = 0; t < 16; ++t) u[t] = s[j + 120 * t];
 #pragma unroll
-                for (int t = 1; t < 16; ++t) u[t] = cmul(u[t], __ldg(&a.tw2[t * 15 + k]));
+                for (int t = 1; t < 16; ++t) u[t] = cmul(u[t], tw2s[t * 15 + k]);
                 bf16(u);
             }
             __syncthreads();
@@ -286,11 +333,20 @@ __global__ void __launch_bounds__(kStft1920Threads, MB) stft1920_kernel(const St
             bf8(u2);
             if (tid < 120) {
                 if (full) {
+                    // bins 1..1919 are all stored: k = j1 + 240 t ascending from p1, M-k descending from p2,
+                    // every address an immediate offset from three per-thread base pointers
+                    const double2 *twp = a.twpost + j1;
+                    double *p1 = out + j1, *p2 = out + (kM1920 - j1);
 #pragma unroll
-                    for (int t = 0; t < 8; ++t) emit_pair<true>(u1[t], u2[7 - t], j1 + 240 * t, a, out, logtab);
+                    for (int t = 0; t < 8; ++t) {
+                        double d1, d2;
+                        untangle_pair(u1[t], u2[7 - t], __ldg(twp + 240 * t), a.scale, logtab, d1, d2);
+                        p1[240 * t] = d1;
+                        p2[-240 * t] = d2;
+                    }
                 } else {
 #pragma unroll
-                    for (int t = 0; t < 8; ++t) emit_pair<false>(u1[t], u2[7 - t], j1 + 240 * t, a, out, logtab);
+                    for (int t = 0; t < 8; ++t) emit_pair(u1[t], u2[7 - t], j1 + 240 * t, a, out, logtab);
                 }
             } else {
 #pragma unroll
@@ -305,11 +361,10 @@ __global__ void __launch_bounds__(kStft1920Threads, MB) stft1920_kernel(const St
                     const int t = (q < 5) ? q : q - 5;
                     const double2 z = (q < 5) ? sp[t] : sp[8 + t];
                     const double2 zr = (q < 5) ? sp[(8 - t) & 7] : sp[15 - t];
-                    emit_pair<false>(z, zr, (q < 5) ? 240 * t : 120 + 240 * t, a, out, logtab);
+                    emit_pair(z, zr, (q < 5) ? 240 * t : 120 + 240 * t, a, out, logtab);
                 }
             }
         }
-        __syncthreads();   // s is rewritten by the next frame's P1
     }
 }
 

@@ -32,7 +32,8 @@ def _dev(t, dtype=None, device=None):
     """Contiguous tensor on the CUDA device (copies host data with a pinned, async H2D when needed)."""
     device = device or require_cuda()
     if isinstance(t, np.ndarray):
-        t = torch.from_numpy(np.ascontiguousarray(t))
+        t = np.ascontiguousarray(t)
+        t = torch.from_numpy(t if t.flags.writeable else t.copy())
     if dtype is not None and t.dtype != dtype:
         t = t.to(dtype)
     if t.device != device:
@@ -45,7 +46,9 @@ def wave_dtype_code(t: torch.Tensor) -> int:
         return _lib.DTYPE_F32
     if t.dtype == _F64:
         return _lib.DTYPE_F64
-    raise TypeError("audio must be float32 or float64, got %s" % t.dtype)
+    if t.dtype == torch.int16:
+        return _lib.DTYPE_I16          # PCM, normalised on the GPU as float32(x)/32767 (from_wave.py:62-66)
+    raise TypeError("audio must be float32, float64 or int16 PCM, got %s" % t.dtype)
 
 
 def stft_db(wave: torch.Tensor, nperseg: int, hop: int, nfft: int, bin_lo: int, bin_hi: int, frame_lo: int,

@@ -241,9 +241,12 @@ class BatchDecodes:
 
 def decode_slots(waves, sample_rate, bins_per_tone: int = 2, steps_per_symbol: int = 2, max_candidates: int = 20,
                  min_score=10, max_iterations: int = 20, freq_min=None, freq_max=None, time_min=None, time_max=None,
-                 chunk_slots: int = 0, return_device: bool = False, piece_slots: int = 512):
+                 chunk_slots: int = 0, return_device: bool = False, piece_slots: int = 512, pcm16: bool = False):
     """Decode a batch of equal-length slots: waves [B, N] (NumPy or torch, host or device, float32/float64).
 
+    With pcm16=True an int16 array is taken as PCM and normalised on the GPU as float32(x)/32767, the way the
+    reference's WAV reader does on the host (src/tests/demodulator/from_wave.py:62-66) - half the host-to-device
+    bytes of float32.  Without it integers are converted to float64 unscaled, as the reference would treat them.
     Per-slot semantics are exactly decode_ft8_message's.  Host input is copied to the GPU inside this
     call (pinned torch tensors copy asynchronously); results come back as a BatchDecodes (host) or, with
     return_device=True, as the engine.SlotDecodes device tensors."""
@@ -251,12 +254,13 @@ def decode_slots(waves, sample_rate, bins_per_tone: int = 2, steps_per_symbol: i
     if isinstance(waves, np.ndarray):
         if np.iscomplexobj(waves):
             raise NotImplementedError("complex input is not covered by the CUDA STFT yet (real audio only)")
-        if waves.dtype not in (np.float32, np.float64):
+        if waves.dtype not in (np.float32, np.float64) and not (pcm16 and waves.dtype == np.int16):
             waves = waves.astype(np.float64)
-        waves = torch.from_numpy(np.ascontiguousarray(waves))
+        waves = np.ascontiguousarray(waves)
+        waves = torch.from_numpy(waves if waves.flags.writeable else waves.copy())
     if waves.dim() == 1:
         waves = waves.reshape(1, -1)
-    if waves.dtype not in (torch.float32, torch.float64):
+    if waves.dtype not in (torch.float32, torch.float64) and not (pcm16 and waves.dtype == torch.int16):
         waves = waves.to(torch.float64)
     B, N = waves.shape
     g = decode_geometry(N, sample_rate, bins_per_tone, steps_per_symbol, freq_min, freq_max, time_min, time_max)

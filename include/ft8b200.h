@@ -21,7 +21,7 @@
  *   - there is NO CPU fallback: without a CUDA device every compute call fails.
  *
  * Layouts (row-major, last index fastest)
- *   wave    [n_slots][slot_stride]            float32 or float64 samples, n_samples used per slot
+ *   wave    [n_slots][slot_stride]            float32 / float64 / int16 samples, n_samples used per slot
  *   mag     [n_slots][T][F]                   dB spectrogram, time-major (the reference's
  *                                             FT8Waterfall.mag is [F][T]; the Python mirror transposes)
  *   scores  [n_slots][nt][nf]                 Costas sync scores in the reference's scan order
@@ -45,6 +45,7 @@ extern "C" {
 
 #define FT8B_DTYPE_F32 0
 #define FT8B_DTYPE_F64 1
+#define FT8B_DTYPE_I16 2   /* int16 PCM, normalised on load as float32(x) / 32767.0f (from_wave.py:62-66) */
 
 #define FT8B_LDPC_N 174
 #define FT8B_LDPC_M 83

@@ -287,6 +287,41 @@ def test_wav_fixture_golden():
     assert [r[3] for r in res] == [550.0, 553.125, 546.875]
 
 
+def test_pcm16_ingest(tmp_path):
+    """int16 PCM normalised on the GPU == the reference's host-side float32(x)/32767 (from_wave.py:62-66)."""
+    import wave
+    from ft8_demodulator_b200 import from_wave
+    g = load_golden("wav_fs20k.npz")
+    pcm = g["samples_int16"]
+    gold = golden_case(g, "f64")
+    kw = dict(bins_per_tone=2, steps_per_symbol=2, max_candidates=20, min_score=10, max_iterations=20, freq_max=1000)
+    a = fd.decode_slots(pcm.reshape(1, -1), int(g["fs"]), pcm16=True, **kw)
+    b = fd.decode_slots((pcm.astype(np.float32) / 32767).reshape(1, -1), int(g["fs"]), **kw)
+    for f in a.arrays.__dataclass_fields__:
+        assert torch.equal(getattr(a.arrays, f), getattr(b.arrays, f)), f
+    check_against_gold(a.arrays, gold)
+    # spectrograms too: fast (nfft 3840) and generic kernels, odd length / unaligned start
+    rng = np.random.default_rng(4)
+    x16 = rng.integers(-32768, 32767, (2, 40001), dtype=np.int16)
+    for fs in (12000, 6000):
+        nperseg, hop, nfft = fd._lib.plan(fs, 2, 2)
+        T = fd._lib.num_frames(40001, nperseg, hop)
+        m16 = engine.stft_db(engine._dev(x16), nperseg, hop, nfft, 0, nfft // 2, 0, T)
+        m32 = engine.stft_db(engine._dev(x16.astype(np.float32) / np.float32(32767)), nperseg, hop, nfft, 0, nfft // 2, 0, T)
+        assert torch.equal(m16, m32)
+    # file path
+    path = str(tmp_path / "fixture.wav")
+    with wave.open(path, "wb") as wf:
+        wf.setnchannels(1); wf.setsampwidth(2); wf.setframerate(int(g["fs"])); wf.writeframes(pcm.tobytes())
+    audio, rate = from_wave.read_wave_file(path)
+    assert rate == int(g["fs"]) and audio.dtype == np.float32 and np.array_equal(audio, pcm.astype(np.float32) / 32767)
+    check_result_list(from_wave.decode_ft8_from_wave(path, freq_max=1000), gold)
+    # without pcm16 an int16 array is plain (unscaled) integers, as the reference would treat it: +90.3 dB everywhere
+    c = fd.decode_slots(pcm.reshape(1, -1), int(g["fs"]), **kw)
+    assert c.arrays.cand_freq[0, :3].tolist() == gold["cand_freq"][:3].tolist()
+    assert bytes(c.arrays.payload[0, 0].numpy()).hex() == "aa0203040506070809f8"
+
+
 @pytest.mark.parametrize("tag,kw", [
     ("k2000_s3", dict(max_candidates=2000, min_score=3, freq_max=3100)),
     ("k20_s3", dict(max_candidates=20, min_score=3, freq_max=3100)),
