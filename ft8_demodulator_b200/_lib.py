@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libft8b200.so")
 
 ERR_ARG, ERR_UNSUPPORTED, ERR_NO_DEVICE = -1, -2, -3
-DTYPE_F32, DTYPE_F64, DTYPE_I16 = 0, 1, 2
+DTYPE_F32, DTYPE_F64, DTYPE_I16, DTYPE_C64, DTYPE_C128 = 0, 1, 2, 3, 4
 MAX_CANDIDATES = 4096
 LDPC_N = 174
 

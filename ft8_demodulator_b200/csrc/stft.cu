@@ -193,6 +193,15 @@ __device__ __forceinline__ double load_sample(const T *x, int i) { return (doubl
 template <>
 __device__ __forceinline__ double load_sample<short>(const short *x, int i) { return (double)__fdiv_rn((float)x[i], 32767.0f); }
 
+template <typename T> struct is_cplx { static constexpr bool value = false; };
+template <> struct is_cplx<float2> { static constexpr bool value = true; };
+template <> struct is_cplx<double2> { static constexpr bool value = true; };
+__device__ __forceinline__ double2 load_cplx(const float2 *x, int i) { const float2 v = x[i]; return make_double2((double)v.x, (double)v.y); }
+__device__ __forceinline__ double2 load_cplx(const double2 *x, int i) { return x[i]; }
+template <typename T> __device__ __forceinline__ double2 load_cplx(const T *, int) { return make_double2(0.0, 0.0); }
+template <> __device__ __forceinline__ double load_sample<float2>(const float2 *, int) { return 0.0; }
+template <> __device__ __forceinline__ double load_sample<double2>(const double2 *, int) { return 0.0; }
+
 // BOUND = the largest block size the instantiation may be launched with (register budget).
 template <typename WaveT, int BOUND>
 __global__ void __launch_bounds__(BOUND, 1) stft_db_kernel(const StftArgs a) {
@@ -206,7 +215,17 @@ __global__ void __launch_bounds__(BOUND, 1) stft_db_kernel(const StftArgs a) {
         const int64_t fr = item - slot * a.frames_out;
         const WaveT *x = reinterpret_cast<const WaveT *>(a.wave) + slot * a.slot_stride + (fr + a.frame_lo) * a.hop;
         // ---- windowed load (zero padded to nfft) ----
-        if (a.even) {
+        if (is_cplx<WaveT>::value) {          // complex audio: plain length-nfft transform, two-sided output
+            for (int n = tid; n < M; n += nthr) {
+                double2 v = make_double2(0.0, 0.0);
+                if (n < a.nperseg) {
+                    const double w = __ldg(&a.win[n]);
+                    const double2 c = load_cplx(x, n);
+                    v = make_double2(w * c.x, w * c.y);
+                }
+                s[n] = v;
+            }
+        } else if (a.even) {
             for (int n = tid; n < M; n += nthr) {
                 const int i0 = 2 * n, i1 = 2 * n + 1;
                 double re = 0.0, im = 0.0;
@@ -273,7 +292,7 @@ static void factorize(int M, int *radix, int *nrad) {
     *nrad = n;
 }
 
-static int get_plan(int nperseg, int nfft, const StftPlan **out) {
+static int get_plan(int nperseg, int nfft, bool cplx, const StftPlan **out) {
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) {
@@ -281,13 +300,13 @@ static int get_plan(int nperseg, int nfft, const StftPlan **out) {
         return FT8B_ERR_NO_DEVICE;
     }
     std::lock_guard<std::mutex> lk(g_plan_mu);
-    auto key = std::make_tuple(dev, nperseg, nfft);
+    auto key = std::make_tuple(dev, nperseg, cplx ? -nfft : nfft);
     auto it = g_plans.find(key);
     if (it != g_plans.end()) { *out = &it->second; return 0; }
     StftPlan p;
     p.nfft = nfft;
     p.nperseg = nperseg;
-    p.even = (nfft % 2 == 0) ? 1 : 0;
+    p.even = (!cplx && nfft % 2 == 0) ? 1 : 0;     // packed real transform; complex input uses the full length
     p.M = p.even ? nfft / 2 : nfft;
     factorize(p.M, p.radix, &p.nrad);
     int nthr = (p.M + 7) / 8;
@@ -332,7 +351,11 @@ static int get_plan(int nperseg, int nfft, const StftPlan **out) {
     FT8B_CUDA_TRY(cudaFuncSetAttribute(stft_db_kernel<double, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     FT8B_CUDA_TRY(cudaFuncSetAttribute(stft_db_kernel<short, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     FT8B_CUDA_TRY(cudaFuncSetAttribute(stft_db_kernel<short, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    if (nperseg == 1920 && nfft == 3840) {
+    FT8B_CUDA_TRY(cudaFuncSetAttribute(stft_db_kernel<float2, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    FT8B_CUDA_TRY(cudaFuncSetAttribute(stft_db_kernel<float2, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    FT8B_CUDA_TRY(cudaFuncSetAttribute(stft_db_kernel<double2, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    FT8B_CUDA_TRY(cudaFuncSetAttribute(stft_db_kernel<double2, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    if (nperseg == 1920 && nfft == 3840 && !cplx) {
         std::vector<double2> t2(16 * 15), t3(8 * 240);
         for (int t = 0; t < 16; ++t)
             for (int k = 0; k < 15; ++k) {
@@ -394,16 +417,18 @@ int stft_db(const void *wave, int wave_dtype, int64_t n_slots, int64_t n_samples
             int hop, int nfft, int bin_lo, int bin_hi, int64_t frame_lo, int64_t frame_hi, double *mag,
             cudaStream_t stream) {
     if (!wave || !mag) FT8B_ARG_FAIL("ft8b_stft_db: null pointer");
-    if (wave_dtype != FT8B_DTYPE_F32 && wave_dtype != FT8B_DTYPE_F64 && wave_dtype != FT8B_DTYPE_I16) FT8B_ARG_FAIL("ft8b_stft_db: bad dtype %d", wave_dtype);
+    if (wave_dtype < FT8B_DTYPE_F32 || wave_dtype > FT8B_DTYPE_C128) FT8B_ARG_FAIL("ft8b_stft_db: bad dtype %d", wave_dtype);
+    const bool cplx = wave_dtype == FT8B_DTYPE_C64 || wave_dtype == FT8B_DTYPE_C128;
     if (nperseg < 1 || hop < 1 || nfft < nperseg) FT8B_ARG_FAIL("ft8b_stft_db: need 1 <= nperseg <= nfft, hop >= 1");
     if (n_slots < 0 || slot_stride < n_samples) FT8B_ARG_FAIL("ft8b_stft_db: bad batch geometry");
     const int64_t T = ft8b_num_frames(n_samples, nperseg, hop);
-    const int max_bin = (nfft % 2 == 0) ? nfft / 2 + 1 : (nfft + 1) / 2;  // bins 0..nfft/2 (even) / 0..(nfft-1)/2 (odd)
+    // real audio: bins 0..nfft/2 (even) / 0..(nfft-1)/2 (odd); complex audio: all nfft bins in natural FFT order
+    const int max_bin = cplx ? nfft : ((nfft % 2 == 0) ? nfft / 2 + 1 : (nfft + 1) / 2);
     if (bin_lo < 0 || bin_hi > max_bin || bin_lo > bin_hi) FT8B_ARG_FAIL("ft8b_stft_db: bin range [%d,%d) outside [0,%d]", bin_lo, bin_hi, max_bin);
     if (frame_lo < 0 || frame_hi > T || frame_lo > frame_hi) FT8B_ARG_FAIL("ft8b_stft_db: frame range outside [0,%lld]", (long long)T);
     if (n_slots == 0 || bin_lo == bin_hi || frame_lo == frame_hi) return 0;
     const StftPlan *plan = nullptr;
-    int rc = get_plan(nperseg, nfft, &plan);
+    int rc = get_plan(nperseg, nfft, cplx, &plan);
     if (rc) return rc;
     const char *force_generic = getenv("FT8B_STFT_GENERIC");
     if (plan->fast && !(force_generic && force_generic[0] == '1')) {
@@ -447,7 +472,13 @@ int stft_db(const void *wave, int wave_dtype, int64_t n_slots, int64_t n_samples
     const int64_t cap = 148 * 64;  // persistent-ish: many CTAs per SM, grid-stride over frames
     if (grid > cap) grid = cap;
     const bool small = plan->nthreads <= 256;
-    if (wave_dtype == FT8B_DTYPE_I16) {
+    if (wave_dtype == FT8B_DTYPE_C64) {
+        if (small) stft_db_kernel<float2, 256><<<(unsigned)grid, plan->nthreads, plan->smem, stream>>>(a);
+        else stft_db_kernel<float2, 1024><<<(unsigned)grid, plan->nthreads, plan->smem, stream>>>(a);
+    } else if (wave_dtype == FT8B_DTYPE_C128) {
+        if (small) stft_db_kernel<double2, 256><<<(unsigned)grid, plan->nthreads, plan->smem, stream>>>(a);
+        else stft_db_kernel<double2, 1024><<<(unsigned)grid, plan->nthreads, plan->smem, stream>>>(a);
+    } else if (wave_dtype == FT8B_DTYPE_I16) {
         if (small) stft_db_kernel<short, 256><<<(unsigned)grid, plan->nthreads, plan->smem, stream>>>(a);
         else stft_db_kernel<short, 1024><<<(unsigned)grid, plan->nthreads, plan->smem, stream>>>(a);
     } else if (wave_dtype == FT8B_DTYPE_F32) {

@@ -48,6 +48,10 @@ def wave_dtype_code(t: torch.Tensor) -> int:
         return _lib.DTYPE_F64
     if t.dtype == torch.int16:
         return _lib.DTYPE_I16          # PCM, normalised on the GPU as float32(x)/32767 (from_wave.py:62-66)
+    if t.dtype == torch.complex64:
+        return _lib.DTYPE_C64
+    if t.dtype == torch.complex128:
+        return _lib.DTYPE_C128
     raise TypeError("audio must be float32, float64 or int16 PCM, got %s" % t.dtype)
 
 

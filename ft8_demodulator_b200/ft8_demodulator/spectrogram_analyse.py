@@ -32,7 +32,8 @@ def time_axis(n_samples: int, nperseg: int, hop: int, sample_rate) -> np.ndarray
 def _as_real_audio(wave_data) -> np.ndarray:
     x = np.asarray(wave_data)
     if np.iscomplexobj(x):
-        raise NotImplementedError("complex input is not covered by the CUDA STFT yet (real audio only)")
+        raise NotImplementedError("the decode path takes real audio (the reference's callers pass np.real(...)); "
+                                  "complex input is supported by calculate_spectrogram only")
     if x.dtype not in (np.float32, np.float64):
         x = x.astype(np.float64)
     return np.ascontiguousarray(x.reshape(-1))
@@ -42,6 +43,8 @@ def calculate_spectrogram(wave_data: np.ndarray, sample_rate: int, bins_per_tone
                           steps_per_symbol: int = 2) -> tuple:
     """dB spectrogram of `wave_data`: (spectrogram[nfft, frames], f[nfft], t[frames])."""
     nperseg, hop, nfft = _lib.plan(sample_rate, bins_per_tone, steps_per_symbol)
+    if np.iscomplexobj(wave_data):
+        return _calculate_spectrogram_complex(np.asarray(wave_data).reshape(-1), sample_rate, nperseg, hop, nfft)
     x = _as_real_audio(wave_data)
     if len(x) < nperseg:                               # spectrogram_analyse.py:37-39
         return np.array([[]]), np.array([]), np.array([])
@@ -58,6 +61,22 @@ def calculate_spectrogram(wave_data: np.ndarray, sample_rate: int, bins_per_tone
         neg = pos[(nfft - 1) // 2:0:-1]
         spec = np.concatenate([neg, pos], axis=0)
     if x.dtype == np.float32:
+        spec = spec.astype(np.float32)
+    return np.ascontiguousarray(spec), frequency_axis(nfft, sample_rate), time_axis(len(x), nperseg, hop, sample_rate)
+
+
+def _calculate_spectrogram_complex(x: np.ndarray, sample_rate, nperseg: int, hop: int, nfft: int) -> tuple:
+    """Complex audio (the satellite pre-processor's input, frequency_correction.py:190-192): full two-sided
+    transform of length nfft on the GPU, fftshifted on the host like spectrogram_analyse.py:63-64."""
+    if len(x) < nperseg:
+        return np.array([[]]), np.array([]), np.array([])
+    if x.dtype != np.complex64:
+        x = x.astype(np.complex128)
+    T = _lib.num_frames(len(x), nperseg, hop)
+    dev = engine.require_cuda()
+    mag = engine.stft_db(engine._dev(np.ascontiguousarray(x).reshape(1, -1), device=dev), nperseg, hop, nfft, 0, nfft, 0, T)
+    spec = np.fft.fftshift(mag[0].transpose(0, 1).cpu().numpy(), axes=0)
+    if x.dtype == np.complex64:
         spec = spec.astype(np.float32)
     return np.ascontiguousarray(spec), frequency_axis(nfft, sample_rate), time_axis(len(x), nperseg, hop, sample_rate)
 

@@ -46,6 +46,8 @@ extern "C" {
 #define FT8B_DTYPE_F32 0
 #define FT8B_DTYPE_F64 1
 #define FT8B_DTYPE_I16 2   /* int16 PCM, normalised on load as float32(x) / 32767.0f (from_wave.py:62-66) */
+#define FT8B_DTYPE_C64 3   /* complex64 (interleaved re,im float32): ft8b_stft_db only, all nfft bins, natural FFT order */
+#define FT8B_DTYPE_C128 4  /* complex128 */
 
 #define FT8B_LDPC_N 174
 #define FT8B_LDPC_M 83
@@ -69,9 +71,10 @@ int ft8b_search_ranges(int T, int F, int time_osr, int freq_osr, int *t0, int *n
  * S1  calculate_spectrogram (spectrogram_analyse.py:19-66 -> scipy.signal.spectrogram, window='hann',
  *     detrend=False, return_onesided=False, scaling='spectrum') fused with the 10*log10(1e-12+|S|) of
  *     :59-60 and with the row/column selection of decode_ft8_message (ft8_decode.py:323-341).
- *     Real input; writes bins [bin_lo, bin_hi) of 0..floor(nfft/2) and frames [frame_lo, frame_hi) as
- *     mag[slot][frame-frame_lo][bin-bin_lo].  The two-sided fftshifted array the reference returns
- *     is the mirror image of these rows (the Python mirror builds it).
+ *     Real input: writes bins [bin_lo, bin_hi) of 0..floor(nfft/2) and frames [frame_lo, frame_hi) as
+ *     mag[slot][frame-frame_lo][bin-bin_lo]; the two-sided fftshifted array the reference returns is the
+ *     mirror image of these rows (the Python mirror builds it).  Complex input (FT8B_DTYPE_C64/C128, the
+ *     satellite pre-processor's case): bins are 0..nfft-1 in natural FFT order; the Python mirror fftshifts.
  */
 int ft8b_stft_db(const void *wave, int wave_dtype, int64_t n_slots, int64_t n_samples, int64_t slot_stride,
                  int nperseg, int hop, int nfft, int bin_lo, int bin_hi, int64_t frame_lo, int64_t frame_hi,
