@@ -33,6 +33,8 @@ int normalize_llr(double *, int64_t, cudaStream_t);
 int ldpc_crc_masked(const double *, const int32_t *, int, int64_t, int, uint8_t *, int32_t *, int32_t *, int32_t *, uint8_t *,
                     cudaStream_t);
 int ldpc_check(const uint8_t *, int64_t, int32_t *, cudaStream_t);
+int column_argmax(const double *, int64_t, int, int, int, int32_t *, cudaStream_t);
+int dechirp(const void *, int, int64_t, double, double, double2 *, cudaStream_t);
 
 // ---- optional per-stage timing (cudaEvent pairs on the launching stream), used by bench.py ----
 constexpr int kStages = 5;   // stft, sync, select, llr, ldpc
@@ -204,6 +206,14 @@ int ft8b_normalize_llr(double *llr, int64_t n_words, void *stream) { return norm
 
 int ft8b_ldpc_check(const uint8_t *bits, int64_t n_words, int32_t *errors, void *stream) {
     return ldpc_check(bits, n_words, errors, (cudaStream_t)stream);
+}
+
+int ft8b_column_argmax(const double *mag, int64_t n_cols, int F, int f_lo, int f_hi, int32_t *idx, void *stream) {
+    return column_argmax(mag, n_cols, F, f_lo, f_hi, idx, (cudaStream_t)stream);
+}
+
+int ft8b_dechirp(const void *in, int in_dtype, int64_t n, double c2, double c3, void *out, void *stream) {
+    return dechirp(in, in_dtype, n, c2, c3, reinterpret_cast<double2 *>(out), (cudaStream_t)stream);
 }
 
 int64_t ft8b_decode_workspace_bytes(const ft8b_decode_params *p, int64_t n_slots, int64_t n_samples) {

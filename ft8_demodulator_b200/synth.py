@@ -240,6 +240,24 @@ def c5_llr(n_words: int, seed: int = 0, snr2500_range=(-26.0, -20.0)):
     return llr, bits
 
 
+def c4_capture(seed: int = 4, fs: int = 12000, f0: float = 300.0, fc: float = 500.0, drift_hz_s: float = 100.0,
+               esn0_db: float = 35.0, payload10: bytes = C1_PAYLOAD) -> np.ndarray:
+    """Config C4 (satellite pass): the recipe of the reference's test_correction.py:185-257 with a seeded RNG.
+    Complex baseband burst at f0, up-converted by fc, zero-padded by its own length on both sides, multiplied by a
+    linear chirp exp(2j*pi*k*n^2/(2 fs^2)) (k in Hz/s), plus complex AWGN with N0 = mean|x|^2 / 10^(EsN0/10),
+    noise power N0*fs split evenly over the real and imaginary parts.  Returns complex128."""
+    bb = ft8_baseband(np.frombuffer(bytes(payload10), dtype=np.uint8), fs, f0)
+    x = bb * np.exp(1j * 2 * np.pi * fc * np.arange(len(bb)) / fs)
+    pad = np.zeros(len(x), dtype=complex)
+    x = np.concatenate((pad, x, pad))
+    n = np.arange(len(x))
+    x = x * np.exp(2j * np.pi * (drift_hz_s / fs) * n ** 2 / (2 * fs))
+    energy = np.sum(np.abs(x) ** 2) / len(x)
+    noise_std = math.sqrt(energy / (10 ** (esn0_db / 10)) * fs / 2)
+    rng = np.random.default_rng(seed)
+    return x + (rng.normal(0, noise_std, len(x)) + 1j * rng.normal(0, noise_std, len(x)))
+
+
 def synth_batch_torch(n_slots: int, device, seed: int = 0, fs: int = 12000, duration_s: float = 15.0,
                       snr_range=(-16.0, -4.0), f0_range=(200.0, 2900.0), start_range=(0.0, 2.0), dtype=None):
     """C3-style batch generated on `device` with torch (plumbing; bench input only).

@@ -134,6 +134,17 @@ int ft8b_normalize_llr(double *llr, int64_t n_words, void *stream);
 int ft8b_ldpc_check(const uint8_t *bits, int64_t n_words, int32_t *errors, void *stream);
 
 /*
+ * Satellite pre-processor correct_frequency_drift (ft8_beacon_receiver/frequency_correction.py:118-659), its two
+ * data-parallel steps; the regression / template-correlation logic around them is scalar host work.
+ *   ft8b_column_argmax: idx[c] = argmax over rows [f_lo, f_hi) of spectrogram column c (first maximum, relative to
+ *                       f_lo), mag laid out [n_cols][F] as ft8b_stft_db writes it            (:222-224, :382-384)
+ *   ft8b_dechirp:       out[n] = in[n] * exp(-2*pi*i*(c2*n^2 + c3*n^3)), in complex64/complex128 (FT8B_DTYPE_C64/
+ *                       C128), out complex128                                                 (:352-355, :598-634)
+ */
+int ft8b_column_argmax(const double *mag, int64_t n_cols, int F, int f_lo, int f_hi, int32_t *idx, void *stream);
+int ft8b_dechirp(const void *in, int in_dtype, int64_t n, double c2, double c3, void *out, void *stream);
+
+/*
  * Whole path, decode_ft8_message (ft8_decode.py:288-394) for a batch of equal-length slots:
  * S1 -> S2a -> S2b -> S3 in chunks of `chunk_slots` slots so the float64 spectrogram and score map of a
  * chunk stay L2-resident between kernels.  `workspace` must hold ft8b_decode_workspace_bytes() bytes.

@@ -237,7 +237,55 @@ def case_rates():
     save("rates.npz", **arrays)
 
 
-CASES = dict(kat=case_kat, c1=case_c1, bp=case_bp, wav=case_wav, c2=case_c2, rates=case_rates)
+def case_c4():
+    """Config C4 (satellite pass): reference correct_frequency_drift + decode of the corrected real part
+    (test_correction.py:281-336 parameters), two geometries."""
+    FC = R.frequency_correction
+    arrays = {}
+    for tag, cfg in (("fs12000_k100", dict(fs=12000, drift_hz_s=100.0, esn0_db=35.0, seed=4)),
+                     ("fs12000_k3", dict(fs=12000, drift_hz_s=3.3, esn0_db=30.0, seed=5)),
+                     ("fs32768_k568", dict(fs=32768, drift_hz_s=568.0, esn0_db=30.0, seed=6))):
+        x = synth.c4_capture(**cfg)
+        ridges, segs = [], []
+        orig_spec, orig_det = FC.calculate_spectrogram, FC.detect_signal_continuity
+
+        def spec(w, fs, b, s):
+            S, f, t = orig_spec(w, fs, b, s)
+            pos = S[f >= 0]
+            ridges.append(np.argmax(pos, axis=0).astype(np.int32))
+            return S, f, t
+
+        def det(idx, window_size=8, max_variance=10.0):
+            out = orig_det(idx, window_size=window_size, max_variance=max_variance)
+            segs.append(np.array(out[0], dtype=np.int64).reshape(-1, 2))
+            return out
+
+        FC.calculate_spectrogram, FC.detect_signal_continuity = spec, det
+        t0 = time.time()
+        try:
+            prm = {'nsync_sym': 7, 'ndata_sym': 58, 'zscore_threshold': 5, 'max_iteration_num': 400000, 'bins_per_tone': 2,
+                   'steps_per_symbol': 8, 'debug_plots': False}
+            with np.errstate(all="ignore"):
+                corrected, rate = R.quiet(FC.correct_frequency_drift, x, cfg["fs"], 6.25, 0.16, prm)
+        finally:
+            FC.calculate_spectrogram, FC.detect_signal_continuity = orig_spec, orig_det
+        t1 = time.time()
+        d = traced_decode(np.real(corrected), cfg["fs"], llr_keep=4, bins_per_tone=2, steps_per_symbol=2, max_candidates=100,
+                          min_score=6, max_iterations=40, time_min=10)
+        arrays.update(prefixed(tag + "__", d))
+        arrays[tag + "__cfg"] = np.array(json.dumps(cfg))
+        arrays[tag + "__input_sha256"] = np.array(sha(x))
+        arrays[tag + "__ridge1"] = ridges[0]
+        arrays[tag + "__ridge2"] = ridges[1] if len(ridges) > 1 else np.zeros(0, np.int32)
+        arrays[tag + "__segments"] = segs[0]
+        arrays[tag + "__drift_per_sample"] = np.array(rate)
+        arrays[tag + "__corrected_probe"] = corrected[::max(1, len(corrected) // 64)][:64]
+        print("   c4 %s: drift %.6g Hz/s (true %.6g), %d decodes (correction %.0f s, decode %.0f s)" % (
+            tag, rate * cfg["fs"], cfg["drift_hz_s"], len(d["res_hash"]), t1 - t0, time.time() - t1))
+    save("c4.npz", **arrays)
+
+
+CASES = dict(c4=case_c4, kat=case_kat, c1=case_c1, bp=case_bp, wav=case_wav, c2=case_c2, rates=case_rates)
 
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)

@@ -48,6 +48,13 @@ class Reference:
             self.gen_crc = importlib.import_module("ft8_tools.ft8_generator.crc")
             self.gen_ldpc = importlib.import_module("ft8_tools.ft8_generator.ldpc")
             self.gen_modulator = importlib.import_module("ft8_tools.ft8_generator.modulator")
+            try:   # needs scikit-learn (present in the build image, absent from the reference's requirements.txt)
+                self.frequency_correction = importlib.import_module("ft8_tools.ft8_beacon_receiver.frequency_correction")
+                import logging
+                logging.getLogger("ft8_tools.ft8_beacon_receiver.frequency_correction").setLevel(logging.CRITICAL)
+                self.frequency_correction.logger.setLevel(logging.CRITICAL)
+            except Exception:   # pragma: no cover
+                self.frequency_correction = None
         self._scratch = tempfile.mkdtemp(prefix="ft8ref_")
 
     def quiet(self, fn, *args, **kwargs):
