@@ -367,9 +367,9 @@ static int get_plan(int nperseg, int nfft, bool cplx, const StftPlan **out) {
                 long double ang = -two_pi * (long double)(t * j) / 1920.0L;
                 t3[t * 240 + j] = make_double2((double)cosl(ang), (double)sinl(ang));
             }
-        std::vector<double2> lt(128);
-        for (int i = 0; i < 128; ++i) {
-            const double inv = 1.0 / (1.0 + ((double)i + 0.5) / 128.0);
+        std::vector<double2> lt(64);
+        for (int i = 0; i < 64; ++i) {
+            const double inv = 1.0 / (1.0 + ((double)i + 0.5) / 64.0);
             lt[i] = make_double2(inv, (double)(-10.0L * log10l((long double)inv)));
         }
         FT8B_CUDA_TRY(cudaMalloc(&p.logtab, sizeof(double2) * lt.size()));

@@ -28,7 +28,7 @@ struct Stft1920Args {
     const double2 *tw2;       // [16][15]  exp(-2*pi*i*t*k/240)
     const double2 *tw3;       // [8][240]  exp(-2*pi*i*t*j/1920)
     const double2 *twpost;    // [1921]    exp(-2*pi*i*k/3840)
-    const double2 *logtab;    // [128]     (1/c_i, 10*log10(c_i)), c_i = 1/fl(1/(1+(i+0.5)/128))
+    const double2 *logtab;    // [64]      (1/c_i, 10*log10(c_i)), c_i = 1/fl(1/(1+(i+0.5)/64))
     double scale;
     int bin_lo, bin_hi;
     int64_t frame_lo, frames_out;
@@ -155,16 +155,18 @@ __device__ __forceinline__ void bf8(double2 (&a)[8]) {
 }
 
 // 10*log10(v) for finite v >= 1e-12 without the libdevice log10 (a division, ~35 FP64 instructions and a
-// slow-path branch per element).  v = 2^e * m, m in [1,2); i = top 7 mantissa bits; r = m * (1/c_i) - 1 with
-// |r| <= 2^-8; 10*log10(v) = e*10*log10(2) + 10*log10(c_i) + (10/ln 10) * (r - r^2/2 + ... + r^7/7).
+// slow-path branch per element).  v = 2^e * m, m in [1,2); i = top 6 mantissa bits; r = m * (1/c_i) - 1 with
+// |r| <= 2^-7; 10*log10(v) = e*10*log10(2) + 10*log10(c_i) + (10/ln 10) * (r - r^2/2 + ... + r^7/7).
 // Max error 2.4e-14 dB against extended precision over [1e-12, 1e4] (np.log10 itself: 1.6e-14 dB).
+// `tab` is this lane's view of the shared table: 8 interleaved copies, entry i of copy q at tab8[i*8 + q], so the
+// 8 lanes of a quarter-warp (one 128-byte shared-memory wavefront for 16-byte loads) never collide.
 __device__ __forceinline__ double fast_db(double v, const double2 *__restrict__ tab) {
     // branch-free: inf / NaN inputs (never produced by finite audio) are patched in at the end with selects
     const long long bits = __double_as_longlong(v);
     const int e = (int)(bits >> 52) - 1023;
-    const int i = (int)(bits >> 45) & 127;
+    const int i = (int)(bits >> 46) & 63;
     const double m = __longlong_as_double((bits & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);
-    const double2 t = tab[i];
+    const double2 t = tab[i * 8];
     const double r = fma(m, t.x, -1.0);
     double p = kK[16];                              // (10/ln10)/7
     p = fma(p, r, kK[17]);                          // -(10/ln10)/6
@@ -221,7 +223,7 @@ __device__ __forceinline__ double to_sample(short v) { return from_pcm16(v); }
 
 template <typename WaveT, bool VEC>
 constexpr size_t stft1920_smem_bytes() {
-    return sizeof(double2) * (kM1920 + 16 + 128 + 16 * 15) + (VEC ? sizeof(WaveT) * kM1920 : 16);
+    return sizeof(double2) * (kM1920 + 16 + 512 + 16 * 15) + (VEC ? sizeof(WaveT) * kM1920 : 16);
 }
 
 // MB = CTAs per SM the register allocation must allow (4: 128 regs, 5: 96 regs, 6: 80 regs)
@@ -231,12 +233,13 @@ __global__ void __launch_bounds__(kStft1920Threads, MB) stft1920_kernel(const St
     extern __shared__ __align__(16) unsigned char smem1920[];     // stft1920_smem_bytes<WaveT, VEC>()
     double2 *s = reinterpret_cast<double2 *>(smem1920);           // [1920] the frame being transformed
     double2 *sp = s + kM1920;                                     // [16]   self-paired butterfly outputs
-    double2 *logtab = sp + 16;                                    // [128]
-    double2 *tw2s = logtab + 128;                                 // [16*15]
+    double2 *logtab8 = sp + 16;                                   // [64][8] interleaved copies of the log table
+    double2 *tw2s = logtab8 + 512;                                // [16*15]
     // VEC path: the next frame's 1920 samples are staged here with cp.async while this frame is transformed
     WaveT *xs = reinterpret_cast<WaveT *>(tw2s + 16 * 15);        // [1920]
     const int tid = threadIdx.x;
-    logtab[tid] = __ldg(&a.logtab[tid]);
+    for (int i = tid; i < 512; i += kStft1920Threads) logtab8[i] = __ldg(&a.logtab[i >> 3]);
+    const double2 *logtab = logtab8 + (tid & 7);                  // this lane's copy
     for (int i = tid; i < 16 * 15; i += kStft1920Threads) tw2s[i] = __ldg(&a.tw2[i]);
     const int64_t n_items = a.n_slots * a.frames_out;
     const int Fout = a.bin_hi - a.bin_lo;

@@ -107,11 +107,13 @@ def _dechirp(wave_dev: torch.Tensor, c2: float, c3: float) -> torch.Tensor:
     return out
 
 
-def correct_frequency_drift(wave_complex: np.ndarray, fs: float, sym_bin: float, sym_t: float, params=None):
+def correct_frequency_drift(wave_complex: np.ndarray, fs: float, sym_bin: float, sym_t: float, params=None, *,
+                            trace: dict = None):
     """Remove linear (and optionally quadratic) frequency drift from a complex FT8 capture.
 
     Same contract as frequency_correction.py:118-659: returns (corrected complex signal at the input rate,
-    estimated drift per sample = Hz/s / fs).  `params` is completed in place with the defaults, as the reference does."""
+    estimated drift per sample = Hz/s / fs).  `params` is completed in place with the defaults, as the reference does.
+    `trace` (extension, keyword only): a dict that receives the intermediate ridge / segment / fit values."""
     if params is None:
         params = dict(DEFAULT_PARAMS)
     else:
@@ -136,6 +138,8 @@ def correct_frequency_drift(wave_complex: np.ndarray, fs: float, sym_bin: float,
     max_freq_indices, freq_bins = _ridge(wave_dev, fs, bins_per_tone, steps_per_symbol)
     max_variance = params['max_variance_factor'] * (freq_bins ** 2)
     signal_segments, _ = detect_signal_continuity(max_freq_indices, window_size=window_size, max_variance=max_variance)
+    if trace is not None:
+        trace.update(ridge1=max_freq_indices, segments=list(signal_segments))
     if not signal_segments:
         return wave_complex, 0.0
     start_idx, end_idx = max(signal_segments, key=lambda s: s[1] - s[0])
@@ -153,6 +157,8 @@ def correct_frequency_drift(wave_complex: np.ndarray, fs: float, sym_bin: float,
             seg_time, seg_freq = seg_time[trim:len(seg_time) - trim], seg_freq[trim:len(seg_freq) - trim]
     _, coefs = _polyfit_coefs(seg_time, seg_freq, 1)
     f_shift_rate = coefs[1]                                            # Hz/s
+    if trace is not None:
+        trace.update(f_shift_rate_linear=float(f_shift_rate))
     lin_dev = _dechirp(wave_dev, f_shift_rate / (2.0 * fs * fs), 0.0)  # exp(-2j*pi*(rate*n^2/2/fs)/fs)
     if not params['precise_sync']:
         return lin_dev.cpu().numpy(), f_shift_rate / fs
@@ -160,6 +166,8 @@ def correct_frequency_drift(wave_complex: np.ndarray, fs: float, sym_bin: float,
     # ---- second ridge, Costas-template time sync on it                                               :364-463
     max_freq_indices_2nd, _ = _ridge(lin_dev, fs, bins_per_tone, steps_per_symbol)
     max_freqs_2nd = max_freq_indices_2nd * freq_step
+    if trace is not None:
+        trace.update(ridge2=max_freq_indices_2nd)
     sync_seq = np.array([3, 1, 4, 0, 6, 5, 2]) + 1
     sync_seq = sync_seq - np.mean(sync_seq)
     samples_per_sym = time_osr * 2
@@ -179,6 +187,8 @@ def correct_frequency_drift(wave_complex: np.ndarray, fs: float, sym_bin: float,
     sync_correlation = np.correlate(masked, three_sync, mode='full')
     peak = int(np.argmax(sync_correlation))
     peak_block = peak - (len(three_sync) - 1) + samples_per_sym // 2
+    if trace is not None:
+        trace.update(sync_block=int(peak_block))
 
     # ---- regression over the three Costas blocks, final de-chirp                                     :505-659
     regression_x, regression_y = np.array([]), np.array([])

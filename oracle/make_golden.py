@@ -242,9 +242,9 @@ def case_c4():
     (test_correction.py:281-336 parameters), two geometries."""
     FC = R.frequency_correction
     arrays = {}
-    for tag, cfg in (("fs12000_k100", dict(fs=12000, drift_hz_s=100.0, esn0_db=35.0, seed=4)),
+    for tag, cfg in (("fs12000_k100", dict(fs=12000, drift_hz_s=100.0, esn0_db=40.0, seed=4)),
                      ("fs12000_k3", dict(fs=12000, drift_hz_s=3.3, esn0_db=30.0, seed=5)),
-                     ("fs32768_k568", dict(fs=32768, drift_hz_s=568.0, esn0_db=30.0, seed=6))):
+                     ("fs32768_k568", dict(fs=32768, drift_hz_s=568.0, esn0_db=35.0, seed=6))):
         x = synth.c4_capture(**cfg)
         ridges, segs = [], []
         orig_spec, orig_det = FC.calculate_spectrogram, FC.detect_signal_continuity
@@ -278,10 +278,10 @@ def case_c4():
         arrays[tag + "__ridge1"] = ridges[0]
         arrays[tag + "__ridge2"] = ridges[1] if len(ridges) > 1 else np.zeros(0, np.int32)
         arrays[tag + "__segments"] = segs[0]
-        arrays[tag + "__drift_per_sample"] = np.array(rate)
+        arrays[tag + "__drift_per_sample"] = np.array(float(np.asarray(rate).ravel()[0]))
         arrays[tag + "__corrected_probe"] = corrected[::max(1, len(corrected) // 64)][:64]
         print("   c4 %s: drift %.6g Hz/s (true %.6g), %d decodes (correction %.0f s, decode %.0f s)" % (
-            tag, rate * cfg["fs"], cfg["drift_hz_s"], len(d["res_hash"]), t1 - t0, time.time() - t1))
+            tag, float(np.asarray(rate).ravel()[0]) * cfg["fs"], cfg["drift_hz_s"], len(d["res_hash"]), t1 - t0, time.time() - t1))
     save("c4.npz", **arrays)
 
 

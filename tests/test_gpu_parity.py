@@ -435,3 +435,57 @@ def test_edge_cases():
     wf = fd.create_waterfall_from_spectrogram(np.zeros((120, 160)), 2, 2)
     c = fd.ft8_find_candidates(wf, 5, 0)
     assert [(x.abs_time, x.abs_freq) for x in c] == [(-20, i) for i in range(5)]
+
+
+# ------------------------------------------------------------------------------------------ satellite pre-processor
+@pytest.mark.parametrize("tag", ["fs12000_k3", "fs12000_k100", "fs32768_k568"])
+def test_drift_correction_golden(tag):
+    """Config C4: correct_frequency_drift + decode of the corrected real part against the reference run recorded in
+    tests/golden/c4.npz (payload-level parity per SURVEY 8d; ridge, segments and drift estimate checked as well)."""
+    import hashlib
+    from ft8_demodulator_b200.ft8_beacon_receiver import frequency_correction as fc
+    g = load_golden("c4.npz")
+    cfg = json.loads(str(g[tag + "__cfg"]))
+    x = synth.c4_capture(**cfg)
+    assert hashlib.sha256(np.ascontiguousarray(x).tobytes()).hexdigest() == str(g[tag + "__input_sha256"])
+    prm = {'nsync_sym': 7, 'ndata_sym': 58, 'zscore_threshold': 5, 'max_iteration_num': 400000, 'bins_per_tone': 2,
+           'steps_per_symbol': 8, 'debug_plots': False}
+    tr = {}
+    corrected, rate = fc.correct_frequency_drift(x, cfg["fs"], 6.25, 0.16, prm, trace=tr)
+    assert np.array_equal(tr["ridge1"], g[tag + "__ridge1"])
+    assert [list(s) for s in tr["segments"]] == g[tag + "__segments"].tolist()
+    assert np.mean(tr["ridge2"] == g[tag + "__ridge2"]) > 0.995        # second ridge sees a 1e-10-different waveform
+    ref_rate = float(g[tag + "__drift_per_sample"])
+    assert abs(rate - ref_rate) <= 1e-6 * abs(ref_rate)
+    assert abs(rate * cfg["fs"] - cfg["drift_hz_s"]) < 0.05 * cfg["drift_hz_s"] + 0.2
+    probe = corrected[::max(1, len(corrected) // 64)][:64]
+    assert corrected.dtype == np.complex128 and np.abs(probe - g[tag + "__corrected_probe"]).max() < 1e-6
+    gold = golden_case(g, tag)
+    kw = dict(bins_per_tone=2, steps_per_symbol=2, max_candidates=100, min_score=6, max_iterations=40, time_min=10)
+    res = fd.decode_ft8_message(np.real(corrected), cfg["fs"], **kw)
+    assert [bytes(m.payload) for m, *_ in res] == [bytes(p) for p in gold["res_payload"]]
+    assert len(res) >= 1 and bytes(res[0][0].payload) == synth.C1_PAYLOAD
+    batch = fd.decode_slots(np.real(corrected).reshape(1, -1), cfg["fs"], **kw)
+    n = int(batch.arrays.n_cand[0])
+    assert batch.arrays.cand_time[0, :n].tolist() == gold["cand_time"].tolist()
+    assert batch.arrays.cand_freq[0, :n].tolist() == gold["cand_freq"].tolist()
+
+
+def test_column_argmax_and_dechirp_kernels():
+    rng = np.random.default_rng(8)
+    mag = rng.standard_normal((3, 50, 333))
+    mag[1, 7, 100] = mag[1, 7, 200] = 9.0                  # tie -> first index, like np.argmax
+    m = engine._dev(mag)
+    idx = torch.zeros((150,), dtype=torch.int32, device=m.device)
+    fd._lib.check(fd._lib.lib().ft8b_column_argmax(m.data_ptr(), 150, 333, 10, 300, idx.data_ptr(), 0))
+    torch.cuda.synchronize()
+    assert idx.cpu().numpy().tolist() == np.argmax(mag.reshape(150, 333)[:, 10:300], axis=1).tolist()
+    from ft8_demodulator_b200.ft8_beacon_receiver import frequency_correction as fc
+    n = 300000
+    x = (rng.standard_normal(n) + 1j * rng.standard_normal(n))
+    c2, c3 = 568.0 / (2 * 32768.0 ** 2), -3.0 / (3 * 32768.0 ** 3)
+    k = np.arange(n, dtype=np.float64)
+    ref = x * np.exp(-2j * np.pi * (c2 * k ** 2 + c3 * k ** 3))
+    for dt in (np.complex128, np.complex64):
+        got = fc._dechirp(engine._dev(x.astype(dt)), c2, c3).cpu().numpy()
+        assert np.abs(got - ref).max() < (1e-8 if dt == np.complex128 else 1e-5)

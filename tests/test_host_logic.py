@@ -137,3 +137,21 @@ def test_pack_records_layout():
     o.payload[1, 2] = torch.arange(10, dtype=torch.uint8)
     rec = fdist.pack_records(o)
     assert rec.shape == (2, 3, 16) and rec[1, 2, 0] == 1 and rec[1, 2, 4] == -7 and rec[1, 2, 6:].tolist() == list(range(10))
+
+
+def test_drift_host_logic_on_golden_ridge():
+    """detect_signal_continuity on the reference's own ridge (tests/golden/c4.npz) reproduces its segments."""
+    from ft8_demodulator_b200.ft8_beacon_receiver import frequency_correction as fc
+    g = load_golden("c4.npz")
+    for tag in ("fs12000_k100", "fs12000_k3", "fs32768_k568"):
+        ridge = g[tag + "__ridge1"]
+        n_pos = {"fs12000": 1920, "fs32768": 5243}[tag.split("_")[0]]
+        segs, metric = fc.detect_signal_continuity(ridge, window_size=4 * 8, max_variance=0.0001 * n_pos ** 2)
+        assert [list(s) for s in segs] == g[tag + "__segments"].tolist()
+        assert len(metric) == len(ridge) - 32 + 1
+    segs, metric = fc.detect_signal_continuity(np.arange(5), window_size=8)
+    assert segs == [] and len(metric) == 5
+    t = np.linspace(-1, 1, 5)
+    assert abs(fc.gfsk_pulse(2.0, t)[2] - 1.0) < 1e-3 and fc.gfsk_pulse(2.0, t)[0] < 0.05
+    ic, c = fc._polyfit_coefs(np.arange(12.0), 1.5 - 0.25 * np.arange(12.0) + 0.125 * np.arange(12.0) ** 2, 2)
+    assert abs(ic - 1.5) < 1e-9 and np.allclose(c, [0, -0.25, 0.125])

@@ -47,3 +47,27 @@ def test_stages_bit_exact_on_reference_spectrogram(ref, orc):
         ok, msg, st = ref.ft8_decode.ft8_decode_candidate(wf, c, 20)
         assert (ok, bytes(msg.payload), st.ldpc_errors, st.crc_extracted, st.crc_calculated) == \
                (r["ok"], r["payload"], r["ldpc_errors"], r["crc_extracted"], r["crc_calculated"])
+
+
+def test_drift_host_logic_vs_reference(ref):
+    """The closed-form continuity metric / fits against the reference's scikit-learn based ones."""
+    from ft8_demodulator_b200.ft8_beacon_receiver import frequency_correction as fc
+    FC = ref.frequency_correction
+    if FC is None:
+        pytest.skip("scikit-learn not available: reference frequency_correction not importable")
+    rng = np.random.default_rng(3)
+    ridge = np.concatenate([rng.integers(0, 1900, 150), np.round(400 + 0.8 * np.arange(300) + rng.normal(0, 0.6, 300)).astype(int),
+                            rng.integers(0, 1900, 120)])
+    a = fc.detect_signal_continuity(ridge, window_size=32, max_variance=0.0001 * 1920 ** 2)
+    b = ref.quiet(FC.detect_signal_continuity, ridge, window_size=32, max_variance=0.0001 * 1920 ** 2)
+    assert [tuple(s) for s in a[0]] == [tuple(s) for s in b[0]]
+    np.testing.assert_allclose(a[1], b[1], rtol=1e-9, atol=1e-9)
+    t = np.linspace(-1, 1, 9)
+    np.testing.assert_array_equal(fc.gfsk_pulse(2.0, t), FC.gfsk_pulse(2.0, t))
+    from sklearn.linear_model import LinearRegression
+    from sklearn.preprocessing import PolynomialFeatures
+    x = np.sort(rng.uniform(10, 25, 40)); y = 3.0 + 0.7 * x - 0.02 * x ** 2 + rng.normal(0, 0.1, 40)
+    for deg in (1, 2):
+        m = LinearRegression().fit(PolynomialFeatures(degree=deg).fit_transform(x.reshape(-1, 1)), y)
+        ic, c = fc._polyfit_coefs(x, y, deg)
+        assert abs(ic - m.intercept_) < 1e-8 and np.allclose(c[1:], m.coef_[1:], rtol=1e-8)
