@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libft8b200.so")
+LIB_PATH = os.environ.get("FT8B_LIB_PATH") or os.path.join(_HERE, "libft8b200.so")   # override: kernel A/B experiments
 
 ERR_ARG, ERR_UNSUPPORTED, ERR_NO_DEVICE = -1, -2, -3
 DTYPE_F32, DTYPE_F64, DTYPE_I16, DTYPE_C64, DTYPE_C128 = 0, 1, 2, 3, 4
