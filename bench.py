@@ -323,7 +323,7 @@ def main():
     # ---- CPU baseline (oracle port) on a bounded sample of the same batch + parity of that sample ----
     cpu = None
     parity = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:      # the CPU leg runs at N=1 only (rank 0)
         threads = cpu_threads()
         sample = args.cpu_sample or max(16, min(512, 6 * threads))
         sample = min(sample, B)

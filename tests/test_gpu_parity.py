@@ -489,3 +489,19 @@ def test_column_argmax_and_dechirp_kernels():
     for dt in (np.complex128, np.complex64):
         got = fc._dechirp(engine._dev(x.astype(dt)), c2, c3).cpu().numpy()
         assert np.abs(got - ref).max() < (1e-8 if dt == np.complex128 else 1e-5)
+
+
+def test_sharded_decode_equals_whole_batch():
+    """slots are independent, so decoding contiguous shards (what each rank of an N-GPU job does) and
+    concatenating gives exactly the single-batch result; the packed records survive pack -> gather order."""
+    from ft8_demodulator_b200 import dist as fdist
+    w, _ = synth.synth_batch_torch(13, dev(), seed=99)
+    kw = dict(bins_per_tone=2, steps_per_symbol=2, max_candidates=20, min_score=1, max_iterations=20)
+    whole = fd.decode_slots(w, 12000, return_device=True, **kw)
+    for world in (2, 3, 8):
+        parts = [fd.decode_slots(w[lo:hi], 12000, return_device=True, **kw)
+                 for lo, hi in (fdist.shard_range(13, r, world) for r in range(world))]
+        for f in whole.__dataclass_fields__:
+            assert torch.equal(torch.cat([getattr(p, f) for p in parts]), getattr(whole, f)), (world, f)
+        recs = torch.cat([fdist.pack_records(p) for p in parts])
+        assert torch.equal(recs, fdist.pack_records(whole))
