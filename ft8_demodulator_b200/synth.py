@@ -116,17 +116,18 @@ def gfsk_frequency_track(itones, fs: float) -> np.ndarray:
     return freq
 
 
-def ft8_baseband(payload10, fs: float, f0: float) -> np.ndarray:
-    """Complex baseband burst, 79*sps samples (modulator.py:56-83): sin(phi) - j cos(phi), 1/8-symbol ramps."""
+def baseband_from_track(freq_track, fs: float, f0: float) -> np.ndarray:
+    """Complex burst from an instantaneous-frequency track (modulator.py:56-75): sin(phi) - j cos(phi) with the
+    sequential fmod phase recursion of :66-68 and the 1/8-symbol raised-cosine ramps of :70-73."""
     sps = int(FT8_SYMBOL_TIME_S * fs)
     n = FT8_SYMBOL_NUM * sps
-    dphi = 2 * np.pi * gfsk_frequency_track(ft8_encode(payload10), fs) / fs + 2 * np.pi * f0 / fs
+    dphi = 2 * np.pi * np.asarray(freq_track, dtype=np.float64) / fs + 2 * np.pi * f0 / fs
     phi = np.empty(n, dtype=np.float64)
     acc = 0.0
     two_pi = 2 * np.pi
     fmod = math.fmod
     dl = dphi.tolist()
-    for i in range(n):           # sequential fmod recursion, exactly as modulator.py:66-68
+    for i in range(n):
         phi[i] = acc
         acc = fmod(acc + dl[i], two_pi)
     wave = np.sin(phi) - 1j * np.cos(phi)
@@ -135,6 +136,11 @@ def ft8_baseband(payload10, fs: float, f0: float) -> np.ndarray:
     wave[:nramp] *= 0.5 * (1 - np.cos(8 * np.pi * i / sps))
     wave[n - 1 - i] *= 0.5 * (1 + np.cos(8 * np.pi * i / sps))
     return wave
+
+
+def ft8_baseband(payload10, fs: float, f0: float) -> np.ndarray:
+    """Complex baseband burst, 79*sps samples (modulator.py:77-83)."""
+    return baseband_from_track(gfsk_frequency_track(ft8_encode(payload10), fs), fs, f0)
 
 
 def ft8_generator(payload10, fs: float, f0: float, fc: float = 0.0) -> np.ndarray:

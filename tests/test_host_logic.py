@@ -155,3 +155,20 @@ def test_drift_host_logic_on_golden_ridge():
     assert abs(fc.gfsk_pulse(2.0, t)[2] - 1.0) < 1e-3 and fc.gfsk_pulse(2.0, t)[0] < 0.05
     ic, c = fc._polyfit_coefs(np.arange(12.0), 1.5 - 0.25 * np.arange(12.0) + 0.125 * np.arange(12.0) ** 2, 2)
     assert abs(ic - 1.5) < 1e-9 and np.allclose(c, [0, -0.25, 0.125])
+
+
+def test_generator_mirror_names():
+    """ft8_generator-compatible names reproduce the reference KATs (tests/golden/kat_encode.json)."""
+    from ft8_demodulator_b200 import ft8_generator as G
+    kat = load_golden("kat_encode.json")
+    for hx, k in kat.items():
+        pl = np.frombuffer(bytes.fromhex(hx), dtype=np.uint8)
+        a91 = G.crc_generator(pl)
+        assert bytes(a91).hex() == k["a91"] and int(G.get_crc_from_a91(a91)) == k["crc"]
+        cw = G.ldpc_generator(a91)
+        assert bytes(cw).hex() == k["codeword"]
+        it = G.itones_generator(G.symbolIdSequence_generator(cw))
+        assert "".join(map(str, it)) == k["itones"] == "".join(map(str, G.ft8_encode(pl)))
+    w = G.ft8_generator(np.frombuffer(synth.C1_PAYLOAD, dtype=np.uint8), 12000, 500, 0)
+    bb = G.ft8_modulation_waveform_generator(G.gfsk_modulation_waveform_generator(G.ft8_encode(synth.C1_PAYLOAD), 12000), 12000, 500)
+    assert np.array_equal(np.real(bb), w) and np.array_equal(G.ft8_baseband_generator(synth.C1_PAYLOAD, 12000, 500), bb)
