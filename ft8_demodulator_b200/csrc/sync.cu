@@ -58,7 +58,7 @@ __device__ __forceinline__ double sync_step(const double (&cur)[8], const double
     double dhi[7], dt[7];
 #pragma unroll
     for (int tau = 0; tau < 7; ++tau) dhi[tau] = __dsub_rn(cur[tau], cur[tau + 1]);
-    // dt[tau] = A[g][tau] - A[g+1][tau] = (p - later); (p - earlier) at the next step is -dt[tau]
+    // dt[tau] = A[g][tau] - A[g+1][tau] = (p - later); (p - earlier) at the next step is -dt[tau] (subtracted there)
     if (HAS_NEXT) {
 #pragma unroll
         for (int tau = 0; tau < 7; ++tau) dt[tau] = __dsub_rn(cur[tau], nxt[tau]);
@@ -69,13 +69,13 @@ __device__ __forceinline__ double sync_step(const double (&cur)[8], const double
     for (int k = 0; k < 7; ++k) {
         const int tau = (k == 0) ? 3 : (k == 1) ? 1 : (k == 2) ? 4 : (k == 3) ? 0 : (k == 4) ? 6 : (k == 5) ? 5 : 2;
         double v = (tau > 0) ? __dadd_rn(-dhi[tau - 1], dhi[tau]) : dhi[0];
-        if (k > 0) v = __dadd_rn(v, dtprev[tau]);              // 0 at the first column
+        if (k > 0) v = __dsub_rn(v, dtprev[tau]);              // (p - earlier) = -(previous step's p - later); 0 at first
         if (k < 6 && HAS_NEXT) v = __dadd_rn(v, dt[tau]);
         G[k] = v;
     }
     if (HAS_NEXT) {
 #pragma unroll
-        for (int tau = 0; tau < 7; ++tau) dtprev[tau] = -dt[tau];
+        for (int tau = 0; tau < 7; ++tau) dtprev[tau] = dt[tau];
     }
     // rotate the block accumulators: acc[k] = S7(h = g-k) through cell k; S7(g-6) completes
     const double done = __dadd_rn(acc[5], G[6]);
@@ -130,72 +130,92 @@ __global__ void __launch_bounds__(kSyncThreads) sync_scores_kernel(const SyncArg
     // by constant strides and wrap with one compare.
     double *const ring_lane = ring + lane;
     double *const ring_end = ring_lane + kSyncStages * ring_w;
-    const double *src = col0 + lane;                     // column min(sg, last), this lane's first bin
-    double *dst = ring_lane;                             // slot sg % kSyncStages
-    int sg = 0;                                          // next column to stage
+    const double *src = col0 + lane;                     // this lane's first bin of the next column to stage
     const bool p0 = lane < f_room;
     const bool p1 = (lane + 32 < ring_w) && (lane + 32 < f_room);
-    auto stage = [&]() {                                 // one commit group per call on every lane
-        if (B > 0) {                                     // ring_w <= 60: at most two 8-byte copies per lane
-            if (p0) __pipeline_memcpy_async(dst, src, 8);
-            if (p1) __pipeline_memcpy_async(dst + 32, src + 32, 8);
-        } else {
-            for (int it = 0, i = lane; it < (ring_w + 31) / 32; ++it, i += 32)
-                if (i < ring_w && i < f_room) __pipeline_memcpy_async(dst + (i - lane), src + (i - lane), 8);
+    // copy column `c` (if it exists) into ring slot `dstp`; exactly one commit group per call on every lane
+    auto stage_to = [&](double *dstp, int c) {
+        if (c <= last) {
+            if (B > 0) {                                 // ring_w <= 60: at most two 8-byte copies per lane
+                if (p0) __pipeline_memcpy_async(dstp, src, 8);
+                if (p1) __pipeline_memcpy_async(dstp + 32, src + 32, 8);
+            } else {
+                for (int it = 0, i = lane; it < (ring_w + 31) / 32; ++it, i += 32)
+                    if (i < ring_w && i < f_room) __pipeline_memcpy_async(dstp + (i - lane), src + (i - lane), 8);
+            }
         }
         __pipeline_commit();
-        if (sg < last) src += rowstep;
-        ++sg;
-        dst += ring_w;
-        if (dst == ring_end) dst = ring_lane;
+        src += rowstep;
     };
     // prologue: columns 0 .. kSyncStages-2 in flight, column 0 landed
 #pragma unroll
-    for (int g = 0; g < kSyncStages - 1; ++g) stage();
+    for (int c = 0; c < kSyncStages - 1; ++c) stage_to(ring_lane + c * ring_w, c);
     __pipeline_wait_prior(kSyncStages - 2);
     __syncwarp();
     if (active) {
 #pragma unroll
         for (int tau = 0; tau < 8; ++tau) ca[tau] = ring_lane[tau * bo];
     }
-    const double *rd = ring_lane + ring_w;               // slot of column g+1
-    double *sp = scp + 4 * kSyncThreads;                 // &score[u = g+4] : target of block m = 0 for h = g-6
-    // Steady state, unrolled by two so `cur`/`nxt` swap by renaming.  At step g: stage column g+4, wait until
-    // column g+1 has landed (3 younger groups may still be in flight), read it, do the arithmetic, then add the
-    // finished block sum S7(h = g-6) into score[u] for u = h+10, h-26, h-62 (m = 0, 1, 2).
-#define FT8B_SYNC_STEP(CUR, NXT, G, HASNEXT)                                                                  \
+    // One step (column gg): stage column gg+4 into slot SLOT_S, wait until column gg+1 (slot SLOT_N) has landed
+    // (3 younger groups may still be in flight), read it, do the arithmetic, add the finished block sum
+    // S7(h = gg-6) into score[u] for u = h+10, h-26, h-62 (m = 0, 1, 2).  SP points at &score[u = gg+4].
+#define FT8B_SYNC_STEP(CUR, NXT, GG, SLOT_S_PTR, SLOT_N_PTR, SP, HASNEXT)                                     \
     do {                                                                                                      \
         __syncwarp();                                                                                         \
-        stage();                                                                                              \
+        stage_to((SLOT_S_PTR), (GG) + kSyncStages - 1);                                                       \
         __pipeline_wait_prior(kSyncStages - 2);                                                               \
         __syncwarp();                                                                                         \
         if (active) {                                                                                         \
             if (HASNEXT) {                                                                                    \
-                _Pragma("unroll") for (int tau = 0; tau < 8; ++tau) NXT[tau] = rd[tau * bo];                  \
+                const double *rp_ = (SLOT_N_PTR);                                                             \
+                _Pragma("unroll") for (int tau = 0; tau < 8; ++tau) NXT[tau] = rp_[tau * bo];                 \
             }                                                                                                 \
             const double done_ = sync_step<HASNEXT>(CUR, NXT, dtprev, acc);                                   \
-            if ((unsigned)((G) + 4) < (unsigned)nu) sp[0] = __dadd_rn(sp[0], done_);                          \
-            if ((unsigned)((G)-32) < (unsigned)nu)                                                            \
-                sp[-kSyncOffset * kSyncThreads] = __dadd_rn(sp[-kSyncOffset * kSyncThreads], done_);          \
-            if ((unsigned)((G)-68) < (unsigned)nu)                                                            \
-                sp[-2 * kSyncOffset * kSyncThreads] = __dadd_rn(sp[-2 * kSyncOffset * kSyncThreads], done_);  \
+            if ((unsigned)((GG) + 4) < (unsigned)nu) (SP)[0] = __dadd_rn((SP)[0], done_);                     \
+            if ((unsigned)((GG)-32) < (unsigned)nu)                                                           \
+                (SP)[-kSyncOffset * kSyncThreads] = __dadd_rn((SP)[-kSyncOffset * kSyncThreads], done_);      \
+            if ((unsigned)((GG)-68) < (unsigned)nu)                                                           \
+                (SP)[-2 * kSyncOffset * kSyncThreads] = __dadd_rn((SP)[-2 * kSyncOffset * kSyncThreads], done_); \
         }                                                                                                     \
-        rd += ring_w;                                                                                         \
-        if (rd == ring_end) rd = ring_lane;                                                                   \
-        sp += kSyncThreads;                                                                                   \
     } while (0)
     int g = 0;
+    if (B > 0) {
+        // Ten steps per trip (lcm of the 5 ring slots and the 2 register buffers): every ring slot, score slot and
+        // buffer role is a compile-time constant, so a step is arithmetic plus a handful of address-free loads.
+        constexpr int RW = 32 + 7 * (B > 0 ? B : 1);
+        for (; g + 10 <= last; g += 10) {
+            double *const sp0 = scp + (g + 4) * kSyncThreads;
+#define FT8B_STEP10(CUR, NXT, O)                                                                              \
+    FT8B_SYNC_STEP(CUR, NXT, g + (O), ring_lane + (((O) + 4) % kSyncStages) * RW,                             \
+                   ring_lane + (((O) + 1) % kSyncStages) * RW, sp0 + (O) * kSyncThreads, true)
+            FT8B_STEP10(ca, cb, 0); FT8B_STEP10(cb, ca, 1); FT8B_STEP10(ca, cb, 2); FT8B_STEP10(cb, ca, 3);
+            FT8B_STEP10(ca, cb, 4); FT8B_STEP10(cb, ca, 5); FT8B_STEP10(ca, cb, 6); FT8B_STEP10(cb, ca, 7);
+            FT8B_STEP10(ca, cb, 8); FT8B_STEP10(cb, ca, 9);
+#undef FT8B_STEP10
+        }
+    }
+    // remaining columns (and the generic freq_osr build): ring slots tracked with wrapping pointers
+    double *dst = ring_lane + ((g + kSyncStages - 1) % kSyncStages) * ring_w;
+    const double *rd = ring_lane + ((g + 1) % kSyncStages) * ring_w;
+    double *sp = scp + (g + 4) * kSyncThreads;
+#define FT8B_ADVANCE()                                                  \
+    do {                                                                \
+        dst += ring_w; if (dst == ring_end) dst = ring_lane;            \
+        rd += ring_w; if (rd == ring_end) rd = ring_lane;               \
+        sp += kSyncThreads;                                             \
+    } while (0)
     for (; g + 2 <= last; g += 2) {
-        FT8B_SYNC_STEP(ca, cb, g, true);
-        FT8B_SYNC_STEP(cb, ca, g + 1, true);
+        FT8B_SYNC_STEP(ca, cb, g, dst, rd, sp, true); FT8B_ADVANCE();
+        FT8B_SYNC_STEP(cb, ca, g + 1, dst, rd, sp, true); FT8B_ADVANCE();
     }
     if (g < last) {                                      // one leftover step with a successor
-        FT8B_SYNC_STEP(ca, cb, g, true);
+        FT8B_SYNC_STEP(ca, cb, g, dst, rd, sp, true); FT8B_ADVANCE();
 #pragma unroll
         for (int tau = 0; tau < 8; ++tau) ca[tau] = cb[tau];
         ++g;
     }
-    FT8B_SYNC_STEP(ca, cb, g, false);                    // g == last
+    FT8B_SYNC_STEP(ca, cb, g, dst, rd, sp, false);       // g == last
+#undef FT8B_ADVANCE
 #undef FT8B_SYNC_STEP
     __pipeline_wait_prior(0);
     if (!active) return;
