@@ -35,6 +35,10 @@ for _p in (ROOT, os.path.join(ROOT, "oracle")):
     if _p not in sys.path:
         sys.path.insert(0, _p)
 
+# keep stdout to the one JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
+
 FS, N_SAMPLES = 12000, 180000
 DECODE_KW = dict(bins_per_tone=2, steps_per_symbol=2, max_candidates=20, min_score=1, max_iterations=20)
 WORKLOAD = ("C3: batch of %d independent synthetic 15-s FT8 slots per GPU, 12 kHz float32, one signal per slot at "

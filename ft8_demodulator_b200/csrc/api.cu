@@ -25,7 +25,9 @@ int sync_scores(const double *, int64_t, int, int, int, int, double *, cudaStrea
 int select_candidates(const double *, int64_t, int, int, int, int, double, int32_t *, int32_t *, double *, int32_t *,
                       int32_t *, cudaStream_t);
 int decode_candidates(const double *, int64_t, int, int, int, int, const int32_t *, const int32_t *, const int32_t *, int,
-                      int, uint8_t *, int32_t *, int32_t *, int32_t *, uint8_t *, double *, uint8_t *, cudaStream_t);
+                      int, uint8_t *, int32_t *, int32_t *, int32_t *, uint8_t *, double *, uint8_t *, const double *,
+                      cudaStream_t);
+int sync_scores_drift(const double *, int64_t, int, int, int, int, int, const double *, double *, int32_t *, cudaStream_t);
 int ldpc_crc(const double *, int64_t, int, uint8_t *, int32_t *, int32_t *, int32_t *, uint8_t *, uint8_t *, cudaStream_t);
 int extract_llr(const double *, int64_t, int, int, int, int, const int32_t *, const int32_t *, const int32_t *, int, int,
                 double *, uint8_t *, int32_t *, cudaStream_t);
@@ -186,7 +188,22 @@ int ft8b_decode_candidates(const double *mag, int64_t n_slots, int T, int F, int
                            int32_t *ldpc_errors, int32_t *crc_extracted, int32_t *crc_calculated, uint8_t *payload,
                            double *llr_out, uint8_t *plain_out, void *stream) {
     return decode_candidates(mag, n_slots, T, F, s, b, cand_time, cand_freq, n_cand, K, max_iterations, ok, ldpc_errors,
-                             crc_extracted, crc_calculated, payload, llr_out, plain_out, (cudaStream_t)stream);
+                             crc_extracted, crc_calculated, payload, llr_out, plain_out, nullptr, (cudaStream_t)stream);
+}
+
+int ft8b_decode_candidates_drift(const double *mag, int64_t n_slots, int T, int F, int s, int b, const int32_t *cand_time,
+                                 const int32_t *cand_freq, const int32_t *n_cand, const double *cand_drift, int K,
+                                 int max_iterations, uint8_t *ok, int32_t *ldpc_errors, int32_t *crc_extracted,
+                                 int32_t *crc_calculated, uint8_t *payload, void *stream) {
+    if (!cand_drift) FT8B_ARG_FAIL("ft8b_decode_candidates_drift: null cand_drift");
+    return decode_candidates(mag, n_slots, T, F, s, b, cand_time, cand_freq, n_cand, K, max_iterations, ok, ldpc_errors,
+                             crc_extracted, crc_calculated, payload, nullptr, nullptr, cand_drift, (cudaStream_t)stream);
+}
+
+int ft8b_sync_scores_drift(const double *mag, int64_t n_slots, int T, int F, int s, int b, int n_hyp,
+                           const double *drift_bins_per_symbol, double *best_score, int32_t *best_hyp, void *stream) {
+    return sync_scores_drift(mag, n_slots, T, F, s, b, n_hyp, drift_bins_per_symbol, best_score, best_hyp,
+                             (cudaStream_t)stream);
 }
 
 int ft8b_ldpc_crc(const double *llr, int64_t n_words, int max_iterations, uint8_t *plain, int32_t *ldpc_errors,

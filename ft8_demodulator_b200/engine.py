@@ -130,6 +130,42 @@ def decode_candidates(mag, time_osr, freq_osr, cand_time, cand_freq, n_cand, max
     return out
 
 
+def sync_scores_drift(mag: torch.Tensor, time_osr: int, freq_osr: int, drift_bins_per_symbol):
+    """Extension: best Costas score over linear-drift hypotheses.  Returns (best_score [B,nt,nf] f64,
+    best_hyp [B,nt,nf] i32, t0)."""
+    assert mag.is_cuda and mag.dtype == _F64 and mag.is_contiguous() and mag.dim() == 3
+    B, T, F = mag.shape
+    t0, nt, nf = _lib.search_ranges(T, F, time_osr, freq_osr)
+    nt, nf = max(nt, 0), max(nf, 0)
+    score = torch.empty((B, nt, nf), dtype=_F64, device=mag.device)
+    hyp = torch.zeros((B, nt, nf), dtype=torch.int32, device=mag.device)
+    d = (C.c_double * len(drift_bins_per_symbol))(*[float(x) for x in drift_bins_per_symbol])
+    if B and nt and nf:
+        _lib.check(_lib.lib().ft8b_sync_scores_drift(_p(mag), B, T, F, time_osr, freq_osr, len(drift_bins_per_symbol), d,
+                                                     _p(score), _p(hyp), _stream()), "ft8b_sync_scores_drift")
+        torch.cuda.current_stream().synchronize()      # the hypothesis table lives in constant memory: one call at a time
+    return score, hyp, t0
+
+
+def decode_candidates_drift(mag, time_osr, freq_osr, cand_time, cand_freq, n_cand, cand_drift, max_iterations) -> CandidateDecodes:
+    """Extension: S3 with the tone grid of each candidate following its drift (bins per symbol)."""
+    assert mag.is_cuda and mag.dtype == _F64 and mag.is_contiguous() and cand_drift.dtype == _F64
+    B, T, F = mag.shape
+    K = cand_time.shape[1]
+    dev = mag.device
+    out = CandidateDecodes(
+        ok=torch.zeros((B, K), dtype=torch.uint8, device=dev), ldpc_errors=torch.zeros((B, K), dtype=torch.int32, device=dev),
+        crc_extracted=torch.zeros((B, K), dtype=torch.int32, device=dev),
+        crc_calculated=torch.zeros((B, K), dtype=torch.int32, device=dev),
+        payload=torch.zeros((B, K, 10), dtype=torch.uint8, device=dev))
+    if B and K:
+        _lib.check(_lib.lib().ft8b_decode_candidates_drift(
+            _p(mag), B, T, F, time_osr, freq_osr, _p(cand_time), _p(cand_freq), _p(n_cand), _p(cand_drift.contiguous()), K,
+            int(max_iterations), _p(out.ok), _p(out.ldpc_errors), _p(out.crc_extracted), _p(out.crc_calculated),
+            _p(out.payload), _stream()), "ft8b_decode_candidates_drift")
+    return out
+
+
 def extract_llr(mag, time_osr, freq_osr, cand_time, cand_freq, n_cand, normalize: bool) -> torch.Tensor:
     B, T, F = mag.shape
     K = cand_time.shape[1]

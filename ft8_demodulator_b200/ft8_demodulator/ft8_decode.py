@@ -279,6 +279,53 @@ def decode_slots(waves, sample_rate, bins_per_tone: int = 2, steps_per_symbol: i
     return BatchDecodes(out.cpu(), sample_rate, bins_per_tone)
 
 
+def decode_slots_drift(waves, sample_rate, drift_hz_per_s, bins_per_tone: int = 2, steps_per_symbol: int = 2,
+                       max_candidates: int = 20, min_score=10, max_iterations: int = 20, freq_min=None, freq_max=None,
+                       time_min=None, time_max=None, slots_per_pass: int = 64):
+    """EXTENSION (not in the reference; BASELINE north_star's drift-hypothesis sync for the satellite path):
+    decode_slots with a Costas search over linear Doppler-drift hypotheses.
+
+    `drift_hz_per_s` lists the hypotheses; 0.0 is always tried first, so a drift-free signal decodes exactly as in
+    decode_slots (with drift_hz_per_s=[0.0] the two functions return identical results).  For hypothesis r the tone
+    grid of symbol q of a candidate is shifted by round(r * 0.16 s * q / bin_width) bins, both in the sync score and
+    in the LLR extraction.  Returns (BatchDecodes, drift_hz_per_s of every candidate as float64 [B, K])."""
+    dev = engine.require_cuda()
+    waves = waves if isinstance(waves, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(np.asarray(waves)))
+    if waves.dim() == 1:
+        waves = waves.reshape(1, -1)
+    if waves.dtype not in (torch.float32, torch.float64):
+        waves = waves.to(torch.float64)
+    B, N = waves.shape
+    K = int(max_candidates)
+    rates = [0.0] + [float(r) for r in drift_hz_per_s if float(r) != 0.0]
+    bin_hz = FT8_SYMBOL_FREQ_INTERVAL_HZ / bins_per_tone
+    d_bins = [r * FT8_SYMBOL_DURATION_S / bin_hz for r in rates]
+    g = decode_geometry(N, sample_rate, bins_per_tone, steps_per_symbol, freq_min, freq_max, time_min, time_max)
+    out = engine.alloc_slot_decodes(B, K, dev)
+    drift = torch.zeros((B, K), dtype=torch.float64, device=dev)
+    if B and g["T_all"] > 0 and g["bin_hi"] > g["bin_lo"] and g["frame_hi"] > g["frame_lo"] and K > 0:
+        rate_t = torch.tensor(rates, dtype=torch.float64, device=dev)
+        dbin_t = torch.tensor(d_bins, dtype=torch.float64, device=dev)
+        for lo in range(0, B, slots_per_pass):
+            hi = min(lo + slots_per_pass, B)
+            w = waves[lo:hi].to(dev).contiguous()
+            mag = engine.stft_db(w, g["nperseg"], g["hop"], g["nfft"], g["bin_lo"], g["bin_hi"], g["frame_lo"], g["frame_hi"])
+            score, hyp, t0 = engine.sync_scores_drift(mag, steps_per_symbol, bins_per_tone, d_bins)
+            if score.numel() == 0:
+                continue
+            ct, cf, cs, nc, _ = engine.select_candidates(score, t0, K, float(min_score))
+            live = torch.arange(K, device=dev)[None, :] < nc[:, None]
+            ti = torch.where(live, ct - t0, torch.zeros_like(ct)).long()
+            h = hyp[torch.arange(hi - lo, device=dev)[:, None], ti, cf.long()].long()      # hypothesis of each candidate
+            dec = engine.decode_candidates_drift(mag, steps_per_symbol, bins_per_tone, ct, cf, nc, dbin_t[h], max_iterations)
+            sl = engine.slice_slot_decodes(out, lo, hi)
+            sl.cand_time.copy_(ct); sl.cand_freq.copy_(cf); sl.cand_score.copy_(cs); sl.n_cand.copy_(nc)
+            sl.ok.copy_(dec.ok); sl.ldpc_errors.copy_(dec.ldpc_errors); sl.crc_extracted.copy_(dec.crc_extracted)
+            sl.crc_calculated.copy_(dec.crc_calculated); sl.payload.copy_(dec.payload)
+            drift[lo:hi] = torch.where(live, rate_t[h], torch.zeros_like(rate_t[h]))
+    return BatchDecodes(out.cpu(), sample_rate, bins_per_tone), drift.cpu().numpy()
+
+
 def decode_ft8_message(wave_data: np.ndarray, sample_rate: int, bins_per_tone: int = 2, steps_per_symbol: int = 2,
                        max_candidates: int = 20, min_score: int = 10, max_iterations: int = 20,
                        freq_min: float = None, freq_max: float = None, time_min: float = None, time_max: float = None
@@ -297,6 +344,6 @@ def decode_ft8_message(wave_data: np.ndarray, sample_rate: int, bins_per_tone: i
 __all__ = [
     "ft8_sync_score", "ft8_find_candidates", "ft8_extract_symbol", "ft8_extract_likelihood", "ftx_normalize_logl",
     "pack_bits", "ftx_compute_crc", "ftx_extract_crc", "ft8_decode_candidate", "create_waterfall_from_spectrogram",
-    "decode_ft8_message", "decode_slots", "decode_geometry", "BatchDecodes", "FT8Waterfall", "FT8Candidate",
+    "decode_ft8_message", "decode_slots", "decode_slots_drift", "decode_geometry", "BatchDecodes", "FT8Waterfall", "FT8Candidate",
     "FT8Message", "FT8DecodeStatus", "FT8Protocol", "bp_decode", "calculate_spectrogram",
 ]

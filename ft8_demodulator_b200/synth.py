@@ -264,6 +264,20 @@ def c4_capture(seed: int = 4, fs: int = 12000, f0: float = 300.0, fc: float = 50
     return x + (rng.normal(0, noise_std, len(x)) + 1j * rng.normal(0, noise_std, len(x)))
 
 
+def drifting_slot(payload10, seed: int, drift_hz_s: float, fs: int = 12000, f0: float = 1000.0, start_s: float = 0.5,
+                  snr_db: float = -8.0, duration_s: float = 15.0) -> np.ndarray:
+    """A 15-s real slot whose burst drifts linearly in frequency (satellite pass, BASELINE config 4: up to
+    +-50 Hz per slot = +-3.33 Hz/s).  Same noise convention as make_slot."""
+    bb = ft8_baseband(np.frombuffer(bytes(payload10), dtype=np.uint8), fs, f0)
+    t = np.arange(len(bb)) / fs
+    w = np.real(bb * np.exp(2j * np.pi * 0.5 * drift_hz_s * t * t))
+    n = int(round(duration_s * fs))
+    slot = embed(w, n, int(round(start_s * fs)))
+    sigma = math.sqrt(float(np.mean(w ** 2)) / 10 ** (snr_db / 10))
+    slot += sigma * np.random.default_rng(seed).standard_normal(n)
+    return slot.astype(np.float32).astype(np.float64)
+
+
 def synth_batch_torch(n_slots: int, device, seed: int = 0, fs: int = 12000, duration_s: float = 15.0,
                       snr_range=(-16.0, -4.0), f0_range=(200.0, 2900.0), start_range=(0.0, 2.0), dtype=None):
     """C3-style batch generated on `device` with torch (plumbing; bench input only).

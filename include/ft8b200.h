@@ -145,6 +145,21 @@ int ft8b_column_argmax(const double *mag, int64_t n_cols, int F, int f_lo, int f
 int ft8b_dechirp(const void *in, int in_dtype, int64_t n, double c2, double c3, void *out, void *stream);
 
 /*
+ * Drift-hypothesis Costas search for the satellite path (EXTENSION named in BASELINE north_star; the reference has no
+ * counterpart, results are checked at payload level only).  drift_bins_per_symbol is a HOST array of n_hyp (<= 128)
+ * hypotheses: the tone grid of symbol q of a candidate is shifted by round(d*q) bins.  best_score/best_hyp
+ * [n_slots][nt][nf]: maximum of ft8_sync_score (ft8_decode.py:47-100, evaluated on the shifted cells) over the
+ * hypotheses and its index (first maximum; list d = 0 first).  ft8b_select_candidates then runs on best_score, and
+ * ft8b_decode_candidates_drift extracts LLRs along each candidate's drift (cand_drift [n_slots][K], bins/symbol).
+ */
+int ft8b_sync_scores_drift(const double *mag, int64_t n_slots, int T, int F, int time_osr, int freq_osr, int n_hyp,
+                           const double *drift_bins_per_symbol, double *best_score, int32_t *best_hyp, void *stream);
+int ft8b_decode_candidates_drift(const double *mag, int64_t n_slots, int T, int F, int time_osr, int freq_osr,
+                                 const int32_t *cand_time, const int32_t *cand_freq, const int32_t *n_cand,
+                                 const double *cand_drift, int K, int max_iterations, uint8_t *ok, int32_t *ldpc_errors,
+                                 int32_t *crc_extracted, int32_t *crc_calculated, uint8_t *payload, void *stream);
+
+/*
  * Whole path, decode_ft8_message (ft8_decode.py:288-394) for a batch of equal-length slots:
  * S1 -> S2a -> S2b -> S3 in chunks of `chunk_slots` slots so the float64 spectrogram and score map of a
  * chunk stay L2-resident between kernels.  `workspace` must hold ft8b_decode_workspace_bytes() bytes.

@@ -505,3 +505,32 @@ def test_sharded_decode_equals_whole_batch():
             assert torch.equal(torch.cat([getattr(p, f) for p in parts]), getattr(whole, f)), (world, f)
         recs = torch.cat([fdist.pack_records(p) for p in parts])
         assert torch.equal(recs, fdist.pack_records(whole))
+
+
+def test_drift_hypothesis_search_extension():
+    """EXTENSION (BASELINE north_star / config 4; no counterpart in the reference, payload-level checks only):
+    (1) with the single hypothesis 0 Hz/s the drift path is exactly the plain pipeline; (2) bursts drifting by
+    +-3.3 Hz/s (+-50 Hz per slot) that the plain search cannot decode are recovered, with the right drift sign."""
+    kw = dict(bins_per_tone=2, steps_per_symbol=2, max_candidates=20, min_score=1, max_iterations=20)
+    plain_in = np.stack([synth.c3_slot(i)[0] for i in range(3)])
+    a = fd.decode_slots(plain_in, 12000, **kw)
+    b, dr = fd.decode_slots_drift(plain_in, 12000, [0.0], **kw)
+    for f in a.arrays.__dataclass_fields__:
+        if f == "cand_score":       # the drift kernel sums in the reference's running order, the main kernel per cell
+            assert (a.arrays.cand_score - b.arrays.cand_score).abs().max().item() < 1e-12
+        else:
+            assert torch.equal(getattr(a.arrays, f), getattr(b.arrays, f)), f
+    assert not dr.any()
+    rates = [3.3, -3.3, 2.0]
+    payloads = [bytes([17 * (i + 1) % 256] * 9 + [0x50]) for i in range(3)]
+    slots = np.stack([synth.drifting_slot(payloads[i], seed=50 + i, drift_hz_s=rates[i], f0=800.0 + 400 * i) for i in range(3)])
+    hyps = np.arange(-4.0, 4.01, 0.25)
+    plain = fd.decode_slots(slots, 12000, **kw)
+    found, drift = fd.decode_slots_drift(slots, 12000, hyps, **kw)
+    for i in range(3):
+        assert payloads[i] not in plain.payload_sets()[i]
+        assert payloads[i] in found.payload_sets()[i]
+        ok = found.arrays.ok[i].numpy().astype(bool)
+        pl = found.arrays.payload[i].numpy()
+        est = [drift[i, c] for c in np.nonzero(ok)[0] if bytes(pl[c]) == payloads[i]]
+        assert any(abs(e - rates[i]) <= 0.75 for e in est), (rates[i], est)
