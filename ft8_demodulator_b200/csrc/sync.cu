@@ -98,7 +98,7 @@ constexpr int kSyncStages = 5;   // spectrogram columns staged per warp: 2 in us
 
 template <int B>
 __global__ void __launch_bounds__(kSyncThreads) sync_scores_kernel(const SyncArgs a) {
-    extern __shared__ double sc[];   // [nu][kSyncThreads] score sums | ring[4 warps][kSyncStages][ring_w] | int ncmp[nu]
+    extern __shared__ double sc[];   // [nu][kSyncThreads] score sums | ring[4 warps][kSyncStages][ring_w] | double2 ncmp[nu]
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int f = blockIdx.x * kSyncThreads + tid;
     const int rho = blockIdx.y;
@@ -107,8 +107,12 @@ __global__ void __launch_bounds__(kSyncThreads) sync_scores_kernel(const SyncArg
     const int bo = (B > 0) ? B : a.b;
     const int ring_w = 32 + 7 * bo;                     // bins a warp touches per column
     double *ring = sc + (size_t)nu * kSyncThreads + (size_t)wid * kSyncStages * ring_w;
-    int *ncmp = reinterpret_cast<int *>(sc + (size_t)nu * kSyncThreads + (size_t)(kSyncThreads / 32) * kSyncStages * ring_w);
-    for (int u = tid; u < nu; u += kSyncThreads) ncmp[u] = sync_num_comparisons(u, nb);
+    // per-u (num_comparisons, 1/num_comparisons) as doubles; (0, 0) when the candidate has no comparison at all
+    double2 *ncmp = reinterpret_cast<double2 *>(sc + (size_t)nu * kSyncThreads + (size_t)(kSyncThreads / 32) * kSyncStages * ring_w);
+    for (int u = tid; u < nu; u += kSyncThreads) {
+        const int n = sync_num_comparisons(u, nb);
+        ncmp[u] = make_double2((double)n, n > 0 ? __drcp_rn((double)n) : 0.0);
+    }
     double *scp = sc + tid;
     for (int u = 0; u < nu; ++u) scp[u * kSyncThreads] = 0.0;
     __syncthreads();
@@ -226,9 +230,16 @@ __global__ void __launch_bounds__(kSyncThreads) sync_scores_kernel(const SyncArg
     double *out = a.scores + slot * (int64_t)(nu * s) * a.nf + (int64_t)rho * a.nf + f;
     const int64_t outstep = (int64_t)s * a.nf;
     for (int u = 0; u < nu; ++u) {
-        const int n = ncmp[u];
+        const double2 nr = ncmp[u];
         double v = scp[u * kSyncThreads];
-        v = (n == 0 || !isfinite(v)) ? -INFINITY : __ddiv_rn(v, (double)n);
+        if (nr.x == 0.0 || !isfinite(v)) {
+            v = -INFINITY;
+        } else {
+            // v / n in three FP64 instructions: q = v*r, one FMA residual step with r = RN(1/n).  Correctly rounded
+            // except for isolated dividends (then off by one ulp) - far inside the 1e-12 score tolerance.
+            const double q = __dmul_rn(v, nr.y);
+            v = fma(fma(-nr.x, q, v), nr.y, q);
+        }
         out[u * outstep] = v;
     }
 }
@@ -421,7 +432,7 @@ int sync_scores(const double *mag, int64_t n_slots, int T, int F, int s, int b, 
     a.mag = mag; a.scores = scores; a.T = T; a.F = F; a.s = s; a.b = b;
     a.nb = T / s; a.nu = nt / s; a.nf = nf;
     const size_t smem = sizeof(double) * ((size_t)a.nu * kSyncThreads + (size_t)(kSyncThreads / 32) * kSyncStages * (32 + 7 * b)) +
-                        sizeof(int) * (size_t)a.nu;
+                        sizeof(double2) * (size_t)a.nu;
     int dev = 0, max_smem = 0;
     FT8B_CUDA_TRY(cudaGetDevice(&dev));
     FT8B_CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
