@@ -386,11 +386,10 @@ static int get_plan(int nperseg, int nfft, bool cplx, const StftPlan **out) {
         if (carve >= 0)                                                                                                \
             cudaFuncSetAttribute(stft1920_kernel<T, MB, V>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);    \
     } while (0)
+        FT8B_STFT1920_ATTR(float, 3, true);  FT8B_STFT1920_ATTR(float, 3, false);
         FT8B_STFT1920_ATTR(float, 4, true);  FT8B_STFT1920_ATTR(float, 4, false);
-        FT8B_STFT1920_ATTR(float, 5, true);  FT8B_STFT1920_ATTR(float, 5, false);
-        FT8B_STFT1920_ATTR(double, 4, true); FT8B_STFT1920_ATTR(double, 4, false);
-        FT8B_STFT1920_ATTR(double, 5, true); FT8B_STFT1920_ATTR(double, 5, false);
-        FT8B_STFT1920_ATTR(short, 4, true);  FT8B_STFT1920_ATTR(short, 4, false);
+        FT8B_STFT1920_ATTR(double, 3, true); FT8B_STFT1920_ATTR(double, 3, false);
+        FT8B_STFT1920_ATTR(short, 3, true);  FT8B_STFT1920_ATTR(short, 3, false);
 #undef FT8B_STFT1920_ATTR
         p.fast = 1;
     }
@@ -437,8 +436,9 @@ int stft_db(const void *wave, int wave_dtype, int64_t n_slots, int64_t n_samples
         f.win = plan->win; f.tw2 = plan->tw2; f.tw3 = plan->tw3; f.twpost = plan->twpost; f.logtab = plan->logtab; f.scale = plan->scale;
         f.bin_lo = bin_lo; f.bin_hi = bin_hi; f.frame_lo = frame_lo; f.frames_out = frame_hi - frame_lo; f.mag = mag;
         const int64_t items = n_slots * f.frames_out;
-        int64_t g1920 = items < 148 * 32 ? items : 148 * 32;
-        static const int mb = [] { const char *e = getenv("FT8B_STFT_MINBLOCKS"); return e ? atoi(e) : 4; }();
+        static const int mb = [] { const char *e = getenv("FT8B_STFT_MINBLOCKS"); return e ? atoi(e) : 3; }();
+        static const int gmul = [] { const char *e = getenv("FT8B_STFT_GRIDMUL"); return e ? atoi(e) : 8; }();
+        int64_t g1920 = items < 148 * mb * gmul ? items : 148 * mb * gmul;
         // vector loads of sample pairs need every frame start to be 2-element aligned
         // the staged path copies sample pairs with cp.async: every frame start must be pair aligned
         const size_t pair_bytes = wave_dtype == FT8B_DTYPE_F32 ? 8 : (wave_dtype == FT8B_DTYPE_I16 ? 4 : 16);
@@ -449,11 +449,11 @@ int stft_db(const void *wave, int wave_dtype, int64_t n_slots, int64_t n_samples
         else stft1920_kernel<T, MB, false><<<(unsigned)g1920, kStft1920Threads, stft1920_smem_bytes<T, false>(), stream>>>(f);     \
     } while (0)
         if (wave_dtype == FT8B_DTYPE_F32) {
-            if (mb == 5) FT8B_STFT1920(float, 5); else FT8B_STFT1920(float, 4);
+            if (mb == 4) FT8B_STFT1920(float, 4); else FT8B_STFT1920(float, 3);
         } else if (wave_dtype == FT8B_DTYPE_I16) {
-            FT8B_STFT1920(short, 4);
+            FT8B_STFT1920(short, 3);
         } else {
-            if (mb == 5) FT8B_STFT1920(double, 5); else FT8B_STFT1920(double, 4);
+            FT8B_STFT1920(double, 3);
         }
 #undef FT8B_STFT1920
         FT8B_LAUNCH_CHECK("stft1920_kernel");
