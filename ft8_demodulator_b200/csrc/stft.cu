@@ -356,16 +356,16 @@ static int get_plan(int nperseg, int nfft, bool cplx, const StftPlan **out) {
     FT8B_CUDA_TRY(cudaFuncSetAttribute(stft_db_kernel<double2, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     FT8B_CUDA_TRY(cudaFuncSetAttribute(stft_db_kernel<double2, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     if (nperseg == 1920 && nfft == 3840 && !cplx) {
-        std::vector<double2> t2(16 * 15), t3(8 * 240);
+        std::vector<double2> t2(16 * 15), t3(8 * kTw3Stride);
         for (int t = 0; t < 16; ++t)
             for (int k = 0; k < 15; ++k) {
                 long double ang = -two_pi * (long double)(t * k) / 240.0L;
                 t2[t * 15 + k] = make_double2((double)cosl(ang), (double)sinl(ang));
             }
         for (int t = 0; t < 8; ++t)
-            for (int j = 0; j < 240; ++j) {
+            for (int j = 0; j <= 240; ++j) {       // column 240 (= W8^t) serves the self-paired butterfly 0, see P3
                 long double ang = -two_pi * (long double)(t * j) / 1920.0L;
-                t3[t * 240 + j] = make_double2((double)cosl(ang), (double)sinl(ang));
+                t3[t * kTw3Stride + j] = make_double2((double)cosl(ang), (double)sinl(ang));
             }
         std::vector<double2> lt(64);
         for (int i = 0; i < 64; ++i) {

@@ -6,7 +6,7 @@
 //   P1 radix 15, Ns = 1   : reads the windowed audio straight from global memory (the upper half of the
 //                           zero-padded frame never exists in memory), writes s[j*15 + f]
 //   P2 radix 16, Ns = 15  : s[j + 120 t] * W240^(t k)  ->  s[(j-k)*16 + k + 15 f]
-//   P3 radix  8, Ns = 240 : thread i owns butterflies i and 240-i, so Z[k] and Z[M-k] meet in registers;
+//   P3 radix  8, Ns = 240 : thread i owns butterflies i+1 and 239-i, so Z[k] and Z[M-k] meet in registers;
 //                           the real-FFT untangling, |X|^2 scaling, +1e-12, 10*log10 and the band crop
 //                           are applied there and the dB values go straight to HBM.
 // Shared-memory traffic per frame is 4 x 30 KB (one write + read per pass boundary), 4 block barriers.
@@ -19,6 +19,7 @@ namespace ft8b {
 
 constexpr int kM1920 = 1920;
 constexpr int kStft1920Threads = 128;
+constexpr int kTw3Stride = 248;     // row pitch of the P3 twiddle table: rows start on 128-byte lines, and not a power of two (L1 sets)
 
 struct Stft1920Args {
     const void *wave;
@@ -26,7 +27,7 @@ struct Stft1920Args {
     int hop;
     const double *win;        // [1920]
     const double2 *tw2;       // [16][15]  exp(-2*pi*i*t*k/240)
-    const double2 *tw3;       // [8][240]  exp(-2*pi*i*t*j/1920)
+    const double2 *tw3;       // [8][kTw3Stride]  exp(-2*pi*i*t*j/1920), j = 0..240
     const double2 *twpost;    // [1921]    exp(-2*pi*i*k/3840)
     const double2 *logtab;    // [64]      (1/c_i, 10*log10(c_i)), c_i = 1/fl(1/(1+(i+0.5)/64))
     double scale;
@@ -199,13 +200,13 @@ __device__ __forceinline__ void untangle_pair(double2 z, double2 zr, double2 w, 
 }
 
 // general form with band crop: stores bins k and M-k when they fall inside [bin_lo, bin_hi)
-__device__ __forceinline__ void emit_pair(double2 z, double2 zr, int k, const Stft1920Args &a, double *out,
+__device__ __forceinline__ void emit_pair(double2 z, double2 zr, int k, bool mirror, const Stft1920Args &a, double *out,
                                           const double2 *__restrict__ tab) {
     double d1, d2;
     untangle_pair(z, zr, __ldg(&a.twpost[k]), a.scale, tab, d1, d2);
     const int k2 = kM1920 - k;
     if (k >= a.bin_lo && k < a.bin_hi) out[k - a.bin_lo] = d1;
-    if (k2 != k && k2 >= a.bin_lo && k2 < a.bin_hi) out[k2 - a.bin_lo] = d2;
+    if (mirror && k2 >= a.bin_lo && k2 < a.bin_hi) out[k2 - a.bin_lo] = d2;
 }
 
 }  // namespace f1920
@@ -227,7 +228,7 @@ __device__ __forceinline__ double to_sample(short v) { return from_pcm16(v); }
 
 template <typename WaveT, bool VEC>
 constexpr size_t stft1920_smem_bytes() {
-    return sizeof(double2) * (kM1920 + 32 + 512 + 16 * 15) + (VEC ? sizeof(WaveT) * kM1920 : 16);
+    return sizeof(double2) * (kM1920 + 512 + 16 * 15) + (VEC ? sizeof(WaveT) * kM1920 : 16);
 }
 
 // MB = CTAs per SM the register allocation must allow.  3 (168 registers, no spills, 12 warps/SM, 92 KB of L1 left
@@ -237,8 +238,7 @@ __global__ void __launch_bounds__(kStft1920Threads, MB) stft1920_kernel(const St
     using namespace f1920;
     extern __shared__ __align__(16) unsigned char smem1920[];     // stft1920_smem_bytes<WaveT, VEC>()
     double2 *s = reinterpret_cast<double2 *>(smem1920);           // [1920] the frame being transformed
-    double2 *sp = s + kM1920;                                     // [16]   self-paired butterfly outputs, [9] their post-twiddles
-    double2 *logtab8 = sp + 32;                                   // [64][8] interleaved copies of the log table
+    double2 *logtab8 = s + kM1920;                                  // [64][8] interleaved copies of the log table
     double2 *tw2s = logtab8 + 512;                                // [16*15]
     // VEC path: the next frame's 1920 samples are staged here with cp.async while this frame is transformed
     WaveT *xs = reinterpret_cast<WaveT *>(tw2s + 16 * 15);        // [1920]
@@ -251,7 +251,6 @@ __global__ void __launch_bounds__(kStft1920Threads, MB) stft1920_kernel(const St
     const double2 *logtab = logtab8 + (tid & 7);                  // this lane's copy
 #endif
     for (int i = tid; i < 16 * 15; i += kStft1920Threads) tw2s[i] = __ldg(&a.tw2[i]);
-    if (tid < 9) sp[16 + tid] = __ldg(&a.twpost[(tid < 5) ? 240 * tid : 120 + 240 * (tid - 5)]);
     const int64_t n_items = a.n_slots * a.frames_out;
     const int Fout = a.bin_hi - a.bin_lo;
     const bool full = (a.bin_lo == 0) && (a.bin_hi >= kM1920);   // bins 0..1919 all stored: no per-bin range checks
@@ -343,56 +342,50 @@ __global__ void __launch_bounds__(kStft1920Threads, MB) stft1920_kernel(const St
         }
         __syncthreads();
         // ---------------- P3: radix 8, Ns = 240, paired butterflies + untangling + dB store
-        // thread i in 0..118 owns butterflies (i+1, 239-i); thread 119 owns the two self-paired ones (0, 120) and
-        // hands their outputs to lanes 119..127 through `sp` so no warp runs a second, divergent copy of the pass.
-        const bool p3_main = tid < 119;
-        if (tid < 120) {
+        // Thread i in 0..118 owns butterflies (i+1, 239-i): outputs u1[t] = Z[k], k = i+1 + 240 t, and u2[7-t] = Z[M-k].
+        // Butterflies 0 and 120 pair with themselves (Z[240 t] with Z[240 ((8-t) & 7)], Z[120 + 240 t] with
+        // Z[120 + 240 (7-t)]).  Threads 119 and 120 run them through the very same instruction stream:
+        //   thread 120: both operands are butterfly 120, u2[7-t] is already the partner;
+        //   thread 119: both are butterfly 0, the second with twiddle column 240 (W8^t), which rotates its outputs
+        //               by one so that u2[7-t] = Z[240 ((8-t) & 7)].
+        // Each of them produces all 8 bins of its butterfly as the "k" output; of the mirrored outputs only the
+        // Nyquist bin (M - 0) is stored.
+        if (tid <= 120) {
             double2 u1[8], u2[8];
-            const int j1 = p3_main ? tid + 1 : 0, j2 = p3_main ? 239 - tid : 120;
+            const bool mirror = tid < 119;                                     // the M-k outputs are ours to store
+            const bool nyquist = tid == 119 && a.bin_hi > kM1920;              // ... or just bin M
+            const int j1 = mirror ? tid + 1 : (tid == 119 ? 0 : 120);
+            const int j2 = mirror ? 239 - tid : j1;                            // row of `s`
+            const int jw2 = (tid == 119) ? 240 : j2;                           // column of tw3
 #pragma unroll
             for (int t = 0; t < 8; ++t) { u1[t] = s[j1 + 240 * t]; u2[t] = s[j2 + 240 * t]; }
 #pragma unroll
             for (int t = 1; t < 8; ++t) {
-                u1[t] = cmul(u1[t], __ldg(&a.tw3[t * 240 + j1]));
-                u2[t] = cmul(u2[t], __ldg(&a.tw3[t * 240 + j2]));
+                u1[t] = cmul(u1[t], __ldg(&a.tw3[t * kTw3Stride + j1]));
+                u2[t] = cmul(u2[t], __ldg(&a.tw3[t * kTw3Stride + jw2]));
             }
             bf8(u1);
             bf8(u2);
-            if (p3_main) {
-                if (full) {
-                    // bins 1..1919 are all stored: k = j1 + 240 t ascending from p1, M-k descending from p2,
-                    // every address an immediate offset from three per-thread base pointers
-                    const double2 *twp = a.twpost + j1;
-                    double *p1 = out + j1, *p2 = out + (kM1920 - j1);
+            if (full) {
+                // bins 0..1919 are all stored: k = j1 + 240 t ascending from p1, M-k descending from p2,
+                // every address an immediate offset from three per-thread base pointers
+                const double2 *twp = a.twpost + j1;
+                double *p1 = out + j1, *p2 = out + (kM1920 - j1);
+                // Both outputs are stored unconditionally (a conditional store would fence each pair into its own
+                // basic block and serialise the log chains): threads 119/120 aim the mirrored value at the slot
+                // the same iteration overwrites with d1 right after.
+                double *const m0 = (mirror || nyquist) ? p2 : p1, *const mt = mirror ? p2 : p1;
+                const int mstep = mirror ? -240 : 240;
 #pragma unroll
-                    for (int t = 0; t < 8; ++t) {
-                        double d1, d2;
-                        untangle_pair(u1[t], u2[7 - t], __ldg(twp + 240 * t), a.scale, logtab, d1, d2);
-                        p1[240 * t] = d1;
-                        p2[-240 * t] = d2;
-                    }
-                } else {
-#pragma unroll
-                    for (int t = 0; t < 8; ++t) emit_pair(u1[t], u2[7 - t], j1 + 240 * t, a, out, logtab);
+                for (int t = 0; t < 8; ++t) {
+                    double d1, d2;
+                    untangle_pair(u1[t], u2[7 - t], __ldg(twp + 240 * t), a.scale, logtab, d1, d2);
+                    if (t == 0) *m0 = d2; else mt[t * mstep] = d2;
+                    p1[240 * t] = d1;
                 }
             } else {
 #pragma unroll
-                for (int t = 0; t < 8; ++t) { sp[t] = u1[t]; sp[8 + t] = u2[t]; }
-            }
-        }
-        if (tid >= 96) {          // warp 3
-            __syncwarp();
-            if (tid >= 119) {
-                // 9 self-pairs, one per lane: q = 0..4 -> (Z[240q], Z[1920-240q]); q = 5..8 -> (Z[120+240t], Z[1800-240t])
-                const int q = tid - 119, t = (q < 5) ? q : q - 5;
-                const int kq = (q < 5) ? 240 * q : 120 + 240 * (q - 5);
-                const double2 z = (q < 5) ? sp[t] : sp[8 + t];
-                const double2 zr = (q < 5) ? sp[(8 - t) & 7] : sp[15 - t];
-                double d1, d2;
-                untangle_pair(z, zr, sp[16 + q], a.scale, logtab, d1, d2);
-                const int k2 = kM1920 - kq;
-                if (kq >= a.bin_lo && kq < a.bin_hi) out[kq - a.bin_lo] = d1;
-                if (k2 != kq && k2 >= a.bin_lo && k2 < a.bin_hi) out[k2 - a.bin_lo] = d2;
+                for (int t = 0; t < 8; ++t) emit_pair(u1[t], u2[7 - t], j1 + 240 * t, mirror || (t == 0 && nyquist), a, out, logtab);
             }
         }
     }
