@@ -48,6 +48,7 @@ SIGNATURES = {
     "ft8b_extract_llr": (_i, [_vp, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "ft8b_normalize_llr": (_i, [_vp, _i64, _vp]),
     "ft8b_ldpc_check": (_i, [_vp, _i64, _vp, _vp]),
+    "ft8b_selfcheck_divide": (_i, [_vp, _vp, _i64, _vp, _vp]),
     "ft8b_column_argmax": (_i, [_vp, _i64, _i, _i, _i, _vp, _vp]),
     "ft8b_dechirp": (_i, [_vp, _i, _i64, _d, _d, _vp, _vp]),
     "ft8b_sync_scores_drift": (_i, [_vp, _i64, _i, _i, _i, _i, _i, C.POINTER(C.c_double), _vp, _vp, _vp]),

@@ -35,6 +35,7 @@ int normalize_llr(double *, int64_t, cudaStream_t);
 int ldpc_crc_masked(const double *, const int32_t *, int, int64_t, int, uint8_t *, int32_t *, int32_t *, int32_t *, uint8_t *,
                     cudaStream_t);
 int ldpc_check(const uint8_t *, int64_t, int32_t *, cudaStream_t);
+int selfcheck_divide(const double *, const double *, int64_t, int64_t *, cudaStream_t);
 int column_argmax(const double *, int64_t, int, int, int, int32_t *, cudaStream_t);
 int dechirp(const void *, int, int64_t, double, double, double2 *, cudaStream_t);
 
@@ -223,6 +224,10 @@ int ft8b_normalize_llr(double *llr, int64_t n_words, void *stream) { return norm
 
 int ft8b_ldpc_check(const uint8_t *bits, int64_t n_words, int32_t *errors, void *stream) {
     return ldpc_check(bits, n_words, errors, (cudaStream_t)stream);
+}
+
+int ft8b_selfcheck_divide(const double *a, const double *b, int64_t n, int64_t *out2, void *stream) {
+    return selfcheck_divide(a, b, n, out2, (cudaStream_t)stream);
 }
 
 int ft8b_column_argmax(const double *mag, int64_t n_cols, int F, int f_lo, int f_hi, int32_t *idx, void *stream) {

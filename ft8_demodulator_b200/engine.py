@@ -211,6 +211,16 @@ def ldpc_check(bits: torch.Tensor) -> torch.Tensor:
     return err
 
 
+def selfcheck_divide(a: torch.Tensor, b: torch.Tensor):
+    """(mismatches, examined) of the BP kernel's branch-free division against IEEE a / b (ft8b_selfcheck_divide)."""
+    assert a.is_cuda and b.is_cuda and a.dtype == _F64 and b.dtype == _F64 and a.is_contiguous() and b.is_contiguous()
+    assert a.numel() == b.numel()
+    out = torch.zeros((2,), dtype=torch.int64, device=a.device)
+    _lib.check(_lib.lib().ft8b_selfcheck_divide(_p(a), _p(b), a.numel(), _p(out), _stream()), "ft8b_selfcheck_divide")
+    bad, seen = out.cpu().tolist()
+    return int(bad), int(seen)
+
+
 # ------------------------------------------------------------------------------------------------
 # Whole path
 # ------------------------------------------------------------------------------------------------

@@ -132,6 +132,13 @@ int ft8b_extract_llr(const double *mag, int64_t n_slots, int T, int F, int time_
 int ft8b_normalize_llr(double *llr, int64_t n_words, void *stream);
 /* ldpc_check (ldpc_decoder.py:33-52): errors[w] = unsatisfied parity checks of bits[w][174] (one byte per bit). */
 int ft8b_ldpc_check(const uint8_t *bits, int64_t n_words, int32_t *errors, void *stream);
+/*
+ * Self-check of the branch-free float64 division the BP kernel uses for fast_tanh / fast_atanh
+ * (ldpc_decoder.py:11-31) against IEEE division: out2[0] = number of i with a differing quotient a[i]/b[i],
+ * out2[1] = number of i examined (operands the kernel would route to its exact fallback are skipped).
+ * The kernel relies on out2[0] == 0 for b in [60, 2.1e4]; tests/test_gpu_parity.py sweeps that domain.
+ */
+int ft8b_selfcheck_divide(const double *a, const double *b, int64_t n, int64_t *out2, void *stream);
 
 /*
  * Satellite pre-processor correct_frequency_drift (ft8_beacon_receiver/frequency_correction.py:118-659), its two

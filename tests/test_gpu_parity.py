@@ -534,3 +534,31 @@ def test_drift_hypothesis_search_extension():
         pl = found.arrays.payload[i].numpy()
         est = [drift[i, c] for c in np.nonzero(ok)[0] if bytes(pl[c]) == payloads[i]]
         assert any(abs(e - rates[i]) <= 0.75 for e in est), (rates[i], est)
+
+
+def test_bp_division_matches_ieee():
+    """The BP kernel's branch-free division (decode.cu div_rn_core) against IEEE division over the operand domain of
+    fast_tanh / fast_atanh (ldpc_decoder.py:11-31): denominators in [60, 2.1e4], numerators of any magnitude."""
+    g = torch.Generator(device="cuda").manual_seed(5)
+    n = 1 << 24
+    total = 0
+    for rep in range(4):
+        # numerators: sign * 2^e * m with e uniform in [-1000, 20]; zeros, NaN and infinities sprinkled in
+        e = torch.randint(-1000, 21, (n,), device="cuda", generator=g, dtype=torch.int64).to(torch.float64)
+        m = 1.0 + torch.rand((n,), device="cuda", generator=g, dtype=torch.float64)
+        sgn = torch.randint(0, 2, (n,), device="cuda", generator=g, dtype=torch.int64).to(torch.float64) * 2 - 1
+        a = sgn * m * torch.exp2(e)
+        a[::1001] = 0.0
+        a[5::4099] = float("nan")
+        a[7::8191] = float("inf")
+        if rep == 0:      # the values BP actually divides: tanh / atanh numerators of O(1) arguments
+            x = (torch.rand((n,), device="cuda", generator=g, dtype=torch.float64) * 2 - 1) * 4.97
+            a = x * (945.0 + x * x * (105.0 + x * x))
+        b = 60.0 + torch.rand((n,), device="cuda", generator=g, dtype=torch.float64) * (2.1e4 - 60.0)
+        if rep == 2:
+            b = 945.0 + torch.rand((n,), device="cuda", generator=g, dtype=torch.float64) * 64.0   # near tanh(0)
+        bad, seen = engine.selfcheck_divide(a.contiguous(), b.contiguous())
+        assert bad == 0
+        assert seen > n // 2
+        total += seen
+    assert total > 3 * n
