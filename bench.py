@@ -158,7 +158,7 @@ def reference_arm(args):
         return 0
     from ft8_demodulator_b200 import synth
     threads = cpu_threads()
-    sample = args.cpu_sample or max(16, min(512, 6 * threads))
+    sample = args.cpu_sample or max(16, min(512, 32 * threads))      # ~3 s of wall clock per step on 16 threads
     waves = np.stack([synth.c3_slot(i)[0] for i in range(sample)]).astype(np.float32)
     for _ in range(args.warmup):
         run_cpu_port(waves[:max(1, min(sample, threads))], threads)
@@ -329,7 +329,7 @@ def main():
     parity = None
     if not args.no_cpu and world == 1:      # the CPU leg runs at N=1 only (rank 0)
         threads = cpu_threads()
-        sample = args.cpu_sample or max(16, min(512, 6 * threads))
+        sample = args.cpu_sample or max(16, min(2048, 128 * threads))    # 10-15 s of wall clock on 16 threads
         sample = min(sample, B)
         wave_s = waves[:sample].cpu().numpy()
         secs, recs = run_cpu_port(wave_s, threads)

@@ -9,7 +9,11 @@ hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 hdr = rows[hi]
 ix = {h: i for i, h in enumerate(hdr)}
 stall = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
-data = [r for r in rows[hi + 1:] if len(r) >= len(hdr)]
+his = [i for i, r in enumerate(rows) if r and r[0] == "Address"]
+sec = int(sys.argv[2]) if len(sys.argv) > 2 else 0          # one section per profiled launch (ncu repeats each twice)
+hi = his[sec]
+end = his[sec + 1] if sec + 1 < len(his) else len(rows)
+data = [r for r in rows[hi + 1:end] if len(r) >= len(hdr)]
 
 
 def num(r, k):

@@ -5,14 +5,17 @@ import sys
 from collections import defaultdict
 
 rows = list(csv.reader(open(sys.argv[1])))
-hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
+his = [i for i, r in enumerate(rows) if r and r[0] == "Address"]
+sec = int(sys.argv[2]) if len(sys.argv) > 2 else 0          # one section per profiled launch (ncu repeats each twice)
+hdr_i = his[sec]
+end_i = his[sec + 1] if sec + 1 < len(his) else len(rows)
 hdr = rows[hdr_i]
 ix = {h: i for i, h in enumerate(hdr)}
 ops = defaultdict(lambda: [0, 0, 0])
 tot = [0, 0]
 stall_cols = [h for h in hdr if h.startswith("stall_")]
 stalls = defaultdict(int)
-for r in rows[hdr_i + 1:]:
+for r in rows[hdr_i + 1:end_i]:
     if len(r) < len(hdr):
         continue
     sass = r[ix["Source"]].strip()
