@@ -86,12 +86,21 @@ __device__ __forceinline__ double sync_step(const double (&cur)[8], const double
 }
 
 // add a finished block sum S7(h) into the scores it belongs to: u = h+10 (m=0), h-26 (m=1), h-62 (m=2)
-__device__ __forceinline__ void sync_scatter(double *scp, int h, int nu, double v) {
+__device__ __forceinline__ void sync_scatter(double *scp, int stride, int h, int nu, double v) {
 #pragma unroll
     for (int m = 0; m < 3; ++m) {
         const unsigned u = (unsigned)(h + 10 - m * kSyncOffset);
-        if (u < (unsigned)nu) scp[u * kSyncThreads] = __dadd_rn(scp[u * kSyncThreads], v);
+        if (u < (unsigned)nu) scp[u * stride] = __dadd_rn(scp[u * stride], v);
     }
+}
+
+// score / num_comparisons, -inf when there was no comparison or the sum is not finite (ft8_decode.py:97-100).
+// nr = (n, RN(1/n)).  v / n in three FP64 instructions: q = v*r and one FMA residual step (Markstein); equal to
+// v / n on all of 8.4e8 random dividends x n = 1..42 tried on the host.
+__device__ __forceinline__ double sync_normalise(double v, double2 nr) {
+    if (nr.x == 0.0 || !isfinite(v)) return -INFINITY;
+    const double q = __dmul_rn(v, nr.y);
+    return fma(fma(-nr.x, q, v), nr.y, q);
 }
 
 constexpr int kSyncStages = 5;   // spectrogram columns staged per warp: 2 in use + 3 in flight
@@ -225,24 +234,18 @@ __global__ void __launch_bounds__(kSyncThreads) sync_scores_kernel(const SyncArg
     if (!active) return;
     // partial blocks that run past the last symbol: h = nb-6 .. nb-1 live in acc[5] .. acc[0]
 #pragma unroll
-    for (int k = 5; k >= 0; --k) sync_scatter(scp, nb - 1 - k, nu, acc[k]);
+    for (int k = 5; k >= 0; --k) sync_scatter(scp, kSyncThreads, nb - 1 - k, nu, acc[k]);
     // normalise and store: score / num_comparisons, -inf when no comparison or non-finite (ft8_decode.py:97-100)
     double *out = a.scores + slot * (int64_t)(nu * s) * a.nf + (int64_t)rho * a.nf + f;
     const int64_t outstep = (int64_t)s * a.nf;
-    for (int u = 0; u < nu; ++u) {
-        const double2 nr = ncmp[u];
-        double v = scp[u * kSyncThreads];
-        if (nr.x == 0.0 || !isfinite(v)) {
-            v = -INFINITY;
-        } else {
-            // v / n in three FP64 instructions: q = v*r, one FMA residual step with r = RN(1/n) (Markstein).  Equal to
-            // v / n on all of 8.4e8 random dividends x n = 1..42 tried on the host.
-            const double q = __dmul_rn(v, nr.y);
-            v = fma(fma(-nr.x, q, v), nr.y, q);
-        }
-        out[u * outstep] = v;
-    }
+    for (int u = 0; u < nu; ++u) out[u * outstep] = sync_normalise(scp[u * kSyncThreads], ncmp[u]);
 }
+
+}  // namespace ft8b
+
+#include "sync_pair.cuh"
+
+namespace ft8b {
 
 // ------------------------------------------------------------------------------------------
 // S2b: selection.  One CTA per slot scans the score map in scan order (flat index = scan order).
@@ -431,31 +434,42 @@ int sync_scores(const double *mag, int64_t n_slots, int T, int F, int s, int b, 
     SyncArgs a;
     a.mag = mag; a.scores = scores; a.T = T; a.F = F; a.s = s; a.b = b;
     a.nb = T / s; a.nu = nt / s; a.nf = nf;
-    const size_t smem = sizeof(double) * ((size_t)a.nu * kSyncThreads + (size_t)(kSyncThreads / 32) * kSyncStages * (32 + 7 * b)) +
-                        sizeof(double2) * (size_t)a.nu;
     int dev = 0, max_smem = 0;
     FT8B_CUDA_TRY(cudaGetDevice(&dev));
     FT8B_CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    if (smem > (size_t)max_smem) {
-        set_error("ft8b_sync_scores: %d time offsets per phase need %zu bytes of shared memory (limit %d)", a.nu, smem, max_smem);
-        return FT8B_ERR_UNSUPPORTED;
-    }
     if (s > 65535 || n_slots > 65535) {
         set_error("ft8b_sync_scores: steps_per_symbol and slots per call must be <= 65535");
         return FT8B_ERR_UNSUPPORTED;
     }
-    dim3 grid((nf + kSyncThreads - 1) / kSyncThreads, s, (unsigned)n_slots);
-#define FT8B_SYNC_LAUNCH(BB)                                                                                         \
+    const char *env_single = getenv("FT8B_SYNC_SINGLE");            // "1": one candidate per thread for every freq_osr
+    const bool single = env_single && env_single[0] == '1';
+    const bool pair = (b == 1 || b == 2 || b == 4) && !single;      // two candidates per thread (sync_pair.cuh)
+    const size_t smem = pair ? (b == 1 ? sync_pair_smem_bytes<1>(a.nu) : b == 2 ? sync_pair_smem_bytes<2>(a.nu) : sync_pair_smem_bytes<4>(a.nu))
+                             : sizeof(double) * ((size_t)a.nu * kSyncThreads + (size_t)(kSyncThreads / 32) * kSyncStages * (32 + 7 * b)) +
+                                   sizeof(double2) * (size_t)a.nu;
+    if (smem > (size_t)max_smem) {
+        set_error("ft8b_sync_scores: %d time offsets per phase need %zu bytes of shared memory (limit %d)", a.nu, smem, max_smem);
+        return FT8B_ERR_UNSUPPORTED;
+    }
+#define FT8B_SYNC_LAUNCH(KERNEL, THREADS, COLS)                                                                      \
     do {                                                                                                             \
-        FT8B_CUDA_TRY(cudaFuncSetAttribute(sync_scores_kernel<BB>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
-                                           (int)max_smem));                                                          \
-        sync_scores_kernel<BB><<<grid, kSyncThreads, smem, stream>>>(a);                                             \
+        dim3 grid((nf + (COLS) - 1) / (COLS), s, (unsigned)n_slots);                                                 \
+        FT8B_CUDA_TRY(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));     \
+        KERNEL<<<grid, THREADS, smem, stream>>>(a);                                                                  \
     } while (0)
-    switch (b) {           // freq_osr as a compile-time constant turns the 8 tone offsets into immediates
-        case 1: FT8B_SYNC_LAUNCH(1); break;
-        case 2: FT8B_SYNC_LAUNCH(2); break;
-        case 4: FT8B_SYNC_LAUNCH(4); break;
-        default: FT8B_SYNC_LAUNCH(0); break;
+    if (pair) {
+        switch (b) {
+            case 1: FT8B_SYNC_LAUNCH(sync_scores_pair_kernel<1>, kPairThreads, kPairCols); break;
+            case 2: FT8B_SYNC_LAUNCH(sync_scores_pair_kernel<2>, kPairThreads, kPairCols); break;
+            default: FT8B_SYNC_LAUNCH(sync_scores_pair_kernel<4>, kPairThreads, kPairCols); break;
+        }
+    } else {
+        switch (b) {       // freq_osr as a compile-time constant turns the 8 tone offsets into immediates
+            case 1: FT8B_SYNC_LAUNCH(sync_scores_kernel<1>, kSyncThreads, kSyncThreads); break;
+            case 2: FT8B_SYNC_LAUNCH(sync_scores_kernel<2>, kSyncThreads, kSyncThreads); break;
+            case 4: FT8B_SYNC_LAUNCH(sync_scores_kernel<4>, kSyncThreads, kSyncThreads); break;
+            default: FT8B_SYNC_LAUNCH(sync_scores_kernel<0>, kSyncThreads, kSyncThreads); break;
+        }
     }
 #undef FT8B_SYNC_LAUNCH
     FT8B_LAUNCH_CHECK("sync_scores_kernel");

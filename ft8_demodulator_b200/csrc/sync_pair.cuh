@@ -1,0 +1,230 @@
+// sync_pair.cuh - S2a for freq_osr B in {1, 2, 4}: the Costas score walk of sync.cu with TWO candidate
+// frequencies per thread, fa and fb = fa + B (one tone apart).
+//
+// Why pairs.  A candidate at f reads the 8 tone bins f + tau*B; its neighbour one tone up reads 7 of the same bins.
+// Walking both in one thread needs 9 bins per column instead of 16, and the frequency differences, time
+// differences and second differences D2[t] = -(A[t-1]-A[t]) + (A[t]-A[t+1]) that both candidates use are formed
+// once: 31 float64 adds per (column, candidate) instead of 41, 4.5 shared-memory loads instead of 8, and all the
+// per-step overhead (cp.async staging, waits, score-slot predicates) is paid once per pair.  Every score is still
+// the same sequence of IEEE additions as in sync_scores_kernel, so the two kernels agree bit for bit.
+//
+// Layout.  A warp owns 64 consecutive candidate frequencies; lane l walks fa = f_warp + (l / B) * 2B + l % B and
+// fb = fa + B.  CTA = 2 warps = 128 frequencies x one time-oversampling phase x one slot (the score sums,
+// [nu][128] float64 in shared memory, cap the occupancy at 4 CTAs per SM either way).  Each warp streams its
+// (64 + 7B)-bin strip through a private 6-column cp.async ring (two columns per commit group, four in flight) and
+// prefetches the tone bins of column g+2 into registers while it does the arithmetic of step g.  Inside a ring column bin i sits at
+// (i % 2B) * PITCH + i / 2B: for a fixed tone offset the 32 lanes then read 32 different banks (bin order would give
+// a 2-way conflict, the lanes of a pair being 2B bins apart).
+#pragma once
+
+namespace ft8b {
+
+constexpr int kPairThreads = 64;
+constexpr int kPairCols = 128;       // candidate frequencies per CTA
+constexpr int kPairStages = 6;       // ring columns per warp, staged two at a time: 2 being read + 4 in flight
+                                     // (8 would push a CTA past the 4-per-SM shared-memory budget)
+
+template <int B>
+struct PairGeom {
+    static constexpr int kStrip = 64 + 7 * B;                               // bins a warp touches per column
+    // plane pitch: >= 96 / 2B so that the 96 staging positions of a column are distinct, and = 8 (B = 2) or 4 (B = 4)
+    // modulo 16 so that the lanes of a half-warp fall into 16 different 8-byte banks
+    static constexpr int kPitch = (B == 1) ? 48 : (B == 2) ? 24 : 20;
+    static constexpr int kCol = 2 * B * kPitch;                             // doubles per ring column
+    __host__ __device__ static constexpr int pos(int i) { return (i % (2 * B)) * kPitch + i / (2 * B); }
+    // offset of tone bin tau relative to the lane's base position pos((l / B) * 2B + l % B)
+    __host__ __device__ static constexpr int tone(int tau) { return B * (tau & 1) * kPitch + tau / 2; }
+};
+
+template <int B>
+size_t sync_pair_smem_bytes(int nu) {
+    return sizeof(double) * ((size_t)nu * kPairCols + (size_t)(kPairThreads / 32) * kPairStages * PairGeom<B>::kCol) +
+           sizeof(double2) * (size_t)nu;
+}
+
+// One symbol step for the pair.  cur/nxt: the 9 tone bins fa + tau*B of columns g and g+1.  Returns the finished
+// block sums S7(g-6) of fa and fb.
+template <bool HAS_NEXT>
+__device__ __forceinline__ void sync_pair_step(const double (&cur)[9], const double (&nxt)[9], double (&dtprev)[9],
+                                               double (&acca)[6], double (&accb)[6], double &done_a, double &done_b) {
+    double dhi[8], dt[9], d2[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) dhi[t] = __dsub_rn(cur[t], cur[t + 1]);
+    if (HAS_NEXT) {
+#pragma unroll
+        for (int t = 0; t < 9; ++t) dt[t] = __dsub_rn(cur[t], nxt[t]);
+    }
+#pragma unroll
+    for (int t = 1; t < 8; ++t) d2[t] = __dadd_rn(-dhi[t - 1], dhi[t]);      // (p - lo) + (p - hi) at bin t
+    double ga[7], gb[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+        const int tau = (k == 0) ? 3 : (k == 1) ? 1 : (k == 2) ? 4 : (k == 3) ? 0 : (k == 4) ? 6 : (k == 5) ? 5 : 2;
+        double va = (tau > 0) ? d2[tau] : dhi[0];          // Costas tone 0 has no lower neighbour (ft8_decode.py:79-82)
+        double vb = (tau > 0) ? d2[tau + 1] : dhi[1];
+        if (k > 0) { va = __dsub_rn(va, dtprev[tau]); vb = __dsub_rn(vb, dtprev[tau + 1]); }      // (p - earlier)
+        if (k < 6 && HAS_NEXT) { va = __dadd_rn(va, dt[tau]); vb = __dadd_rn(vb, dt[tau + 1]); }  // (p - later)
+        ga[k] = va;
+        gb[k] = vb;
+    }
+    if (HAS_NEXT) {
+#pragma unroll
+        for (int t = 0; t < 9; ++t) dtprev[t] = dt[t];
+    }
+    done_a = __dadd_rn(acca[5], ga[6]);
+    done_b = __dadd_rn(accb[5], gb[6]);
+#pragma unroll
+    for (int k = 5; k >= 1; --k) {
+        acca[k] = __dadd_rn(acca[k - 1], ga[k]);
+        accb[k] = __dadd_rn(accb[k - 1], gb[k]);
+    }
+    acca[0] = ga[0];
+    accb[0] = gb[0];
+}
+
+// add the finished block sums S7(h = g-6) of step g into score[u] for u = h+10, h-26, h-62 (m = 0, 1, 2);
+// sp = &score[u = g+4] of fa, fb sits 32 doubles further
+__device__ __forceinline__ void sync_pair_scatter(double *sp, int g, int nu, double da, double db) {
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+        if ((unsigned)(g + 4 - m * kSyncOffset) < (unsigned)nu) {
+            double *q = sp - m * kSyncOffset * kPairCols;
+            q[0] = __dadd_rn(q[0], da);
+            q[32] = __dadd_rn(q[32], db);
+        }
+    }
+}
+
+template <int B>
+__global__ void __launch_bounds__(kPairThreads) sync_scores_pair_kernel(const SyncArgs a) {
+    using G = PairGeom<B>;
+    extern __shared__ double sc[];   // [nu][128] score sums | ring[2 warps][kPairStages][kCol] | double2 ncmp[nu]
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int rho = blockIdx.y;
+    const int64_t slot = blockIdx.z;
+    const int nb = a.nb, nu = a.nu, s = a.s;
+    double *const ring = sc + (size_t)nu * kPairCols + (size_t)wid * kPairStages * G::kCol;
+    double *const ring_end = ring + kPairStages * G::kCol;
+    double2 *ncmp = reinterpret_cast<double2 *>(sc + (size_t)nu * kPairCols + (size_t)(kPairThreads / 32) * kPairStages * G::kCol);
+    for (int u = tid; u < nu; u += kPairThreads) {
+        const int n = sync_num_comparisons(u, nb);
+        ncmp[u] = make_double2((double)n, n > 0 ? __drcp_rn((double)n) : 0.0);
+    }
+    // score sums of this thread: fa in column wid*64 + lane, fb 32 columns further (both conflict-free)
+    double *scp = sc + wid * 64 + lane;
+    for (int u = 0; u < nu; ++u) { scp[u * kPairCols] = 0.0; scp[u * kPairCols + 32] = 0.0; }
+    __syncthreads();
+    const int f_warp = (blockIdx.x * (kPairThreads / 32) + wid) * 64;
+    if (f_warp >= a.nf) return;
+    const int base = (lane / B) * 2 * B + lane % B;      // fa - f_warp
+    const int fa = f_warp + base, fb = fa + B;
+    const int last = nb - 1;
+
+    // ---- staging: lane copies strip bins lane, lane+32, lane+64 of a column into their swizzled ring positions.
+    // Every lane always issues its three 8-byte cp.async; a copy that has no source (beyond the strip, the row or the
+    // last column) is issued with 0 source bytes (it writes zeros) - no branch, no divergence.
+    const double *col0 = a.mag + slot * (int64_t)a.T * a.F + (int64_t)rho * a.F + f_warp;
+    const int64_t rowstep = (int64_t)s * a.F;
+    const int f_room = a.F - f_warp;
+    const bool c0 = lane < f_room, c1 = lane + 32 < f_room, c2 = (lane + 64 < G::kStrip) && (lane + 64 < f_room);
+    const int d0 = G::pos(lane), d1 = G::pos(lane + 32), d2o = G::pos(lane + 64);
+    const double *src = col0 + lane;                     // this lane's first bin of the next column to stage
+    double *wr = ring;                                   // ring slot of the next column to stage
+    int staged = 0;                                      // next column to stage
+    auto stage_col = [&]() {
+        const bool live = staged <= last;
+        const double *p = live ? src : a.mag;
+        __pipeline_memcpy_async(wr + d0, (live && c0) ? p : a.mag, 8, (live && c0) ? 0 : 8);
+        __pipeline_memcpy_async(wr + d1, (live && c1) ? p + 32 : a.mag, 8, (live && c1) ? 0 : 8);
+        __pipeline_memcpy_async(wr + d2o, (live && c2) ? p + 64 : a.mag, 8, (live && c2) ? 0 : 8);
+        src += rowstep;
+        ++staged;
+        wr += G::kCol;
+        if (wr == ring_end) wr = ring;
+    };
+    auto stage_two = [&]() { stage_col(); stage_col(); __pipeline_commit(); };
+
+    // ---- registers: three column buffers rotate (cur, nxt, the one being prefetched)
+    double ra[9], rb[9], rc[9], dtprev[9], acca[6], accb[6];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) dtprev[k] = 0.0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { acca[k] = 0.0; accb[k] = 0.0; }
+    const double *rd = ring + G::pos(base);              // this lane's tone-0 position in the ring slot to read next
+    const double *const rd_end = rd + kPairStages * G::kCol;
+#define FT8B_PAIR_LOAD(BUF)                                                                  \
+    do {                                                                                     \
+        _Pragma("unroll") for (int tau = 0; tau < 9; ++tau) BUF[tau] = rd[G::tone(tau)];     \
+        rd += G::kCol;                                                                       \
+        if (rd == rd_end) rd -= kPairStages * G::kCol;                                       \
+    } while (0)
+    // prologue: columns 0..5 in flight as three groups, columns 0 and 1 landed and in registers
+    stage_two(); stage_two(); stage_two();
+    __pipeline_wait_prior(kPairStages / 2 - 1);
+    __syncwarp();
+    FT8B_PAIR_LOAD(ra);
+    FT8B_PAIR_LOAD(rb);
+
+    // A trip of two steps (columns g, g+1): stage columns g+6, g+7 into the slots of columns g, g+1 (read during the
+    // previous trip), wait until columns g+2, g+3 have landed (two younger groups may be in flight), then each step
+    // prefetches the column after its successor while doing its arithmetic.
+#define FT8B_PAIR_STEP(CUR, NXT, PRE, O)                                                     \
+    do {                                                                                     \
+        FT8B_PAIR_LOAD(PRE);                                                                 \
+        double da_, db_;                                                                     \
+        sync_pair_step<true>(CUR, NXT, dtprev, acca, accb, da_, db_);                        \
+        sync_pair_scatter(sp0 + (O) * kPairCols, g + (O), nu, da_, db_);                     \
+    } while (0)
+#define FT8B_PAIR_TRIP(X, Y, Z, O)                                                           \
+    do {                                                                                     \
+        __syncwarp();                                                                        \
+        stage_two();                                                                         \
+        __pipeline_wait_prior(kPairStages / 2 - 1);                                                          \
+        __syncwarp();                                                                        \
+        FT8B_PAIR_STEP(X, Y, Z, O);                                                          \
+        FT8B_PAIR_STEP(Y, Z, X, (O) + 1);                                                    \
+    } while (0)
+    int g = 0;
+    for (; g + 6 <= last; g += 6) {                      // six steps: the three register buffers are back in place
+        double *const sp0 = scp + (g + 4) * kPairCols;
+        FT8B_PAIR_TRIP(ra, rb, rc, 0);
+        FT8B_PAIR_TRIP(rc, ra, rb, 2);
+        FT8B_PAIR_TRIP(rb, rc, ra, 4);
+    }
+#undef FT8B_PAIR_TRIP
+#undef FT8B_PAIR_STEP
+    // at most six columns are left and all of them are already in the ring or on their way
+    __pipeline_wait_prior(0);
+    __syncwarp();
+    for (; g <= last; ++g) {
+        double da, db;
+        if (g < last) {
+            FT8B_PAIR_LOAD(rc);                          // column g+2 (unused garbage when there is none)
+            sync_pair_step<true>(ra, rb, dtprev, acca, accb, da, db);
+        } else {
+            sync_pair_step<false>(ra, rb, dtprev, acca, accb, da, db);
+        }
+        sync_pair_scatter(scp + (g + 4) * kPairCols, g, nu, da, db);
+#pragma unroll
+        for (int tau = 0; tau < 9; ++tau) { ra[tau] = rb[tau]; rb[tau] = rc[tau]; }
+    }
+#undef FT8B_PAIR_LOAD
+    // partial blocks that run past the last symbol: h = nb-6 .. nb-1 live in acc[5] .. acc[0]
+#pragma unroll
+    for (int k = 5; k >= 0; --k) {
+        sync_scatter(scp, kPairCols, nb - 1 - k, nu, acca[k]);
+        sync_scatter(scp + 32, kPairCols, nb - 1 - k, nu, accb[k]);
+    }
+    // normalise and store: score / num_comparisons, -inf when no comparison or non-finite (ft8_decode.py:97-100)
+    double *out = a.scores + slot * (int64_t)(nu * s) * a.nf + (int64_t)rho * a.nf;
+    const int64_t outstep = (int64_t)s * a.nf;
+    const bool va = fa < a.nf, vb = fb < a.nf;
+    for (int u = 0; u < nu; ++u) {
+        const double2 nr = ncmp[u];
+        const double xa = scp[u * kPairCols], xb = scp[u * kPairCols + 32];
+        if (va) out[u * outstep + fa] = sync_normalise(xa, nr);
+        if (vb) out[u * outstep + fb] = sync_normalise(xb, nr);
+    }
+}
+
+}  // namespace ft8b

@@ -562,3 +562,19 @@ def test_bp_division_matches_ieee():
         assert seen > n // 2
         total += seen
     assert total > 3 * n
+
+
+@pytest.mark.parametrize("b,s,F,T", [(2, 2, 1920, 186), (1, 1, 961, 93), (4, 2, 700, 190), (2, 4, 333, 371), (1, 2, 65, 120)])
+def test_sync_pair_kernel_equals_single_kernel(monkeypatch, b, s, F, T):
+    """Two candidates per thread (sync_pair.cuh) against one per thread (sync.cu): the same IEEE additions in the same
+    order, so the score maps must be identical bit for bit - including ragged widths and -inf entries."""
+    g = torch.Generator(device="cuda").manual_seed(b * 100 + s)
+    mag = torch.randn((3, T, F), device="cuda", dtype=torch.float64, generator=g) * 10 - 40
+    mag[1, 5, 7] = float("inf")
+    mag[2, 40:44, :] = float("nan")
+    pair, _ = engine.sync_scores(mag, s, b)
+    monkeypatch.setenv("FT8B_SYNC_SINGLE", "1")
+    single, _ = engine.sync_scores(mag, s, b)
+    monkeypatch.delenv("FT8B_SYNC_SINGLE")
+    assert pair.shape == single.shape and pair.numel() > 0
+    assert torch.equal(pair.view(torch.int64), single.view(torch.int64))
