@@ -95,12 +95,14 @@ __device__ __forceinline__ void sync_scatter(double *scp, int stride, int h, int
 }
 
 // score / num_comparisons, -inf when there was no comparison or the sum is not finite (ft8_decode.py:97-100).
-// nr = (n, RN(1/n)).  v / n in three FP64 instructions: q = v*r and one FMA residual step (Markstein); equal to
-// v / n on all of 8.4e8 random dividends x n = 1..42 tried on the host.
+// nr = (n, RN(1/n)), (0, 0) when n = 0.  v / n in three FP64 instructions: q = v*r and one FMA residual step
+// (Markstein); equal to v / n on all of 8.4e8 random dividends x n = 1..42 tried on the host.  Branch-free, so the
+// unrolled store loops keep several of these chains in flight.
 __device__ __forceinline__ double sync_normalise(double v, double2 nr) {
-    if (nr.x == 0.0 || !isfinite(v)) return -INFINITY;
     const double q = __dmul_rn(v, nr.y);
-    return fma(fma(-nr.x, q, v), nr.y, q);
+    const double r = fma(fma(-nr.x, q, v), nr.y, q);
+    const bool bad = (__double2hiint(nr.y) == 0) | (((unsigned)__double2hiint(v) & 0x7ff00000u) == 0x7ff00000u);
+    return bad ? -INFINITY : r;
 }
 
 constexpr int kSyncStages = 5;   // spectrogram columns staged per warp: 2 in use + 3 in flight
@@ -238,6 +240,7 @@ __global__ void __launch_bounds__(kSyncThreads) sync_scores_kernel(const SyncArg
     // normalise and store: score / num_comparisons, -inf when no comparison or non-finite (ft8_decode.py:97-100)
     double *out = a.scores + slot * (int64_t)(nu * s) * a.nf + (int64_t)rho * a.nf + f;
     const int64_t outstep = (int64_t)s * a.nf;
+#pragma unroll 4
     for (int u = 0; u < nu; ++u) out[u * outstep] = sync_normalise(scp[u * kSyncThreads], ncmp[u]);
 }
 

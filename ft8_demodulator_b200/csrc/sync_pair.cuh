@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(kPairThreads) sync_scores_pair_kernel(const Sy
 
     // ---- staging: lane copies strip bins lane, lane+32, lane+64 of a column into their swizzled ring positions.
     // Every lane always issues its three 8-byte cp.async; a copy that has no source (beyond the strip, the row or the
-    // last column) is issued with 0 source bytes (it writes zeros) - no branch, no divergence.
+    // last column) is issued with 0 source bytes (nothing is read, zeros are written) - no branch, no divergence.
     const double *col0 = a.mag + slot * (int64_t)a.T * a.F + (int64_t)rho * a.F + f_warp;
     const int64_t rowstep = (int64_t)s * a.F;
     const int f_room = a.F - f_warp;
@@ -131,12 +131,12 @@ __global__ void __launch_bounds__(kPairThreads) sync_scores_pair_kernel(const Sy
     const double *src = col0 + lane;                     // this lane's first bin of the next column to stage
     double *wr = ring;                                   // ring slot of the next column to stage
     int staged = 0;                                      // next column to stage
+    const int z0 = c0 ? 0 : 8, z1 = c1 ? 0 : 8, z2 = c2 ? 0 : 8;      // source bytes to skip (8 = copy nothing)
     auto stage_col = [&]() {
         const bool live = staged <= last;
-        const double *p = live ? src : a.mag;
-        __pipeline_memcpy_async(wr + d0, (live && c0) ? p : a.mag, 8, (live && c0) ? 0 : 8);
-        __pipeline_memcpy_async(wr + d1, (live && c1) ? p + 32 : a.mag, 8, (live && c1) ? 0 : 8);
-        __pipeline_memcpy_async(wr + d2o, (live && c2) ? p + 64 : a.mag, 8, (live && c2) ? 0 : 8);
+        __pipeline_memcpy_async(wr + d0, src, 8, live ? z0 : 8);
+        __pipeline_memcpy_async(wr + d1, src + 32, 8, live ? z1 : 8);
+        __pipeline_memcpy_async(wr + d2o, src + 64, 8, live ? z2 : 8);
         src += rowstep;
         ++staged;
         wr += G::kCol;
@@ -216,14 +216,20 @@ __global__ void __launch_bounds__(kPairThreads) sync_scores_pair_kernel(const Sy
         sync_scatter(scp + 32, kPairCols, nb - 1 - k, nu, accb[k]);
     }
     // normalise and store: score / num_comparisons, -inf when no comparison or non-finite (ft8_decode.py:97-100)
-    double *out = a.scores + slot * (int64_t)(nu * s) * a.nf + (int64_t)rho * a.nf;
-    const int64_t outstep = (int64_t)s * a.nf;
+    // (a candidate beyond nf - 1 has nothing to store: its pointer is parked on the warp's first column, which lane 0
+    // owns, and the predicate keeps it from writing)
     const bool va = fa < a.nf, vb = fb < a.nf;
+    double *oa = a.scores + slot * (int64_t)(nu * s) * a.nf + (int64_t)rho * a.nf + (va ? fa : f_warp);
+    double *ob = oa + (vb ? fb : f_warp) - (va ? fa : f_warp);
+    const int64_t outstep = (int64_t)s * a.nf;
+#pragma unroll 4
     for (int u = 0; u < nu; ++u) {
         const double2 nr = ncmp[u];
-        const double xa = scp[u * kPairCols], xb = scp[u * kPairCols + 32];
-        if (va) out[u * outstep + fa] = sync_normalise(xa, nr);
-        if (vb) out[u * outstep + fb] = sync_normalise(xb, nr);
+        const double ya = sync_normalise(scp[u * kPairCols], nr), yb = sync_normalise(scp[u * kPairCols + 32], nr);
+        if (va) *oa = ya;
+        if (vb) *ob = yb;
+        oa += outstep;
+        ob += outstep;
     }
 }
 
