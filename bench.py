@@ -48,6 +48,9 @@ STFT_BYTES_PER_SLOT = 180000 * 4 + 1920 * 186 * 8      # read audio f32 + write 
 SYNC_BYTES_PER_SLOT = 1920 * 186 * 8 + 88 * 1906 * 8   # read dB f64 + write score map f64
 SELECT_BYTES_PER_SLOT = 88 * 1906 * 8
 LDPC_BYTES_PER_WORD = 174 * 8 + 10 + 1 + 3 * 4
+# SURVEY.md 8d quotes the same stages for a float32 spectrogram (a design this repo rejects);
+# reported next to the float64 figures so both readings of the contract are on the line
+SURVEY_FP32_BYTES = {"stft_db": 180000 * 4 + 1920 * 186 * 4, "costas_sync": 1920 * 186 * 4 + 20 * 12 + 4}
 STAGES = ["stft_db", "costas_sync", "select", "llr", "ldpc_crc"]
 
 
@@ -366,6 +369,11 @@ def main():
             "unit": "GB/s", "frac": stages[STAGES[dom]]["achieved_gbs"] / peak,
             "traffic": (tps * slots_per_launch) if (tps and dom < 3) else None, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": alg[dom] * units[dom] / max(sn[dom], 1),
+            "algorithmic_bytes_per_slot": alg[dom] if dom < 3 else None,
+            "survey_fp32_layout": ({"bytes_per_slot": SURVEY_FP32_BYTES[STAGES[dom]],
+                                    "achieved": SURVEY_FP32_BYTES[STAGES[dom]] * units[dom] / (sm[dom] * 1e-3) / 1e9,
+                                    "frac": SURVEY_FP32_BYTES[STAGES[dom]] * units[dom] / (sm[dom] * 1e-3) / 1e9 / peak}
+                                   if STAGES[dom] in SURVEY_FP32_BYTES else None),
             "avg_launch_ms": sm[dom] / max(sn[dom], 1),
             "note": "float64 FFT/stencil/BP kernels are bound by the FP64 pipe and shared memory, not HBM (DESIGN.md)"}
 

@@ -76,11 +76,12 @@ struct StageScope {
 };
 
 static int default_chunk_slots(int64_t per_slot_bytes) {
-    // Enough slots per launch to fill 148 SMs several times over in every stage; the kernels are bound by
-    // the FP64 pipe, not HBM, so L2 residency of the chunk's spectrogram is secondary.
-    int64_t c = (2048ll << 20) / (per_slot_bytes > 0 ? per_slot_bytes : 1);
+    // The kernels are bound by the FP64 pipe, not HBM, so L2 residency of a chunk is not the point; larger chunks
+    // mean fewer launches and shorter tails (measured on 4096 slots: 188k / 206k / 214k slots/s at 128 / 487 / 2048).
+    // Cap the chunk workspace at 8 GiB of the 180 GB.
+    int64_t c = (8192ll << 20) / (per_slot_bytes > 0 ? per_slot_bytes : 1);
     if (c < 1) c = 1;
-    if (c > 512) c = 512;
+    if (c > 2048) c = 2048;
     return (int)c;
 }
 

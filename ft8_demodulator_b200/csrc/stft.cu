@@ -378,16 +378,12 @@ static int get_plan(int nperseg, int nfft, bool cplx, const StftPlan **out) {
         FT8B_CUDA_TRY(cudaMalloc(&p.tw3, sizeof(double2) * t3.size()));
         FT8B_CUDA_TRY(cudaMemcpy(p.tw2, t2.data(), sizeof(double2) * t2.size(), cudaMemcpyHostToDevice));
         FT8B_CUDA_TRY(cudaMemcpy(p.tw3, t3.data(), sizeof(double2) * t3.size(), cudaMemcpyHostToDevice));
-        static const int carve = [] { const char *e = getenv("FT8B_STFT_CARVEOUT"); return e ? atoi(e) : -1; }();
 #define FT8B_STFT1920_ATTR(T, MB, V)                                                                                   \
     do {                                                                                                               \
         FT8B_CUDA_TRY(cudaFuncSetAttribute(stft1920_kernel<T, MB, V>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
                                            (int)stft1920_smem_bytes<T, V>()));                                         \
-        if (carve >= 0)                                                                                                \
-            cudaFuncSetAttribute(stft1920_kernel<T, MB, V>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);    \
     } while (0)
         FT8B_STFT1920_ATTR(float, 3, true);  FT8B_STFT1920_ATTR(float, 3, false);
-        FT8B_STFT1920_ATTR(float, 4, true);  FT8B_STFT1920_ATTR(float, 4, false);
         FT8B_STFT1920_ATTR(double, 3, true); FT8B_STFT1920_ATTR(double, 3, false);
         FT8B_STFT1920_ATTR(short, 3, true);  FT8B_STFT1920_ATTR(short, 3, false);
 #undef FT8B_STFT1920_ATTR
@@ -436,9 +432,9 @@ int stft_db(const void *wave, int wave_dtype, int64_t n_slots, int64_t n_samples
         f.win = plan->win; f.tw2 = plan->tw2; f.tw3 = plan->tw3; f.twpost = plan->twpost; f.logtab = plan->logtab; f.scale = plan->scale;
         f.bin_lo = bin_lo; f.bin_hi = bin_hi; f.frame_lo = frame_lo; f.frames_out = frame_hi - frame_lo; f.mag = mag;
         const int64_t items = n_slots * f.frames_out;
-        static const int mb = [] { const char *e = getenv("FT8B_STFT_MINBLOCKS"); return e ? atoi(e) : 3; }();
-        static const int gmul = [] { const char *e = getenv("FT8B_STFT_GRIDMUL"); return e ? atoi(e) : 8; }();
-        int64_t g1920 = items < 148 * mb * gmul ? items : 148 * mb * gmul;
+        // persistent CTAs: 3 per SM x 148 SMs, 8 waves so that the tail of the grid-stride loop stays short
+        constexpr int64_t kGrid1920 = 148 * 3 * 8;
+        const int64_t g1920 = items < kGrid1920 ? items : kGrid1920;
         // vector loads of sample pairs need every frame start to be 2-element aligned
         // the staged path copies sample pairs with cp.async: every frame start must be pair aligned
         const size_t pair_bytes = wave_dtype == FT8B_DTYPE_F32 ? 8 : (wave_dtype == FT8B_DTYPE_I16 ? 4 : 16);
@@ -449,7 +445,7 @@ int stft_db(const void *wave, int wave_dtype, int64_t n_slots, int64_t n_samples
         else stft1920_kernel<T, MB, false><<<(unsigned)g1920, kStft1920Threads, stft1920_smem_bytes<T, false>(), stream>>>(f);     \
     } while (0)
         if (wave_dtype == FT8B_DTYPE_F32) {
-            if (mb == 4) FT8B_STFT1920(float, 4); else FT8B_STFT1920(float, 3);
+            FT8B_STFT1920(float, 3);
         } else if (wave_dtype == FT8B_DTYPE_I16) {
             FT8B_STFT1920(short, 3);
         } else {

@@ -167,11 +167,7 @@ __device__ __forceinline__ double fast_db(double v, const double2 *__restrict__ 
     const int e = (int)(bits >> 52) - 1023;
     const int i = (int)(bits >> 46) & 63;
     const double m = __longlong_as_double((bits & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);
-#ifdef FT8B_STFT_LOG1
-    const double2 t = tab[i];
-#else
     const double2 t = tab[i * 8];
-#endif
     const double r = fma(m, t.x, -1.0);
     double p = kK[16];                              // (10/ln10)/7
     p = fma(p, r, kK[17]);                          // -(10/ln10)/6
@@ -184,8 +180,6 @@ __device__ __forceinline__ double fast_db(double v, const double2 *__restrict__ 
     return (__double2hiint(v) >= 0x7ff00000) ? v + v : res;  // +inf -> +inf, NaN -> NaN (as 10*log10 would); v > 0
 }
 
-// Untangle the pair (Z[k], Z[M-k]) of the packed transform and emit dB for bins k and M-k
-// (spectrogram_analyse.py:59-60: 10*log10(1e-12 + |S|), S = |X|^2 / (sum w)^2).
 // Untangle the pair (Z[k], Z[M-k]) of the packed transform into dB for bins k and M-k
 // (spectrogram_analyse.py:59-60: 10*log10(1e-12 + |S|), S = |X|^2 / (sum w)^2).
 __device__ __forceinline__ void untangle_pair(double2 z, double2 zr, double2 w, double scale, const double2 *__restrict__ tab,
@@ -244,12 +238,7 @@ __global__ void __launch_bounds__(kStft1920Threads, MB) stft1920_kernel(const St
     WaveT *xs = reinterpret_cast<WaveT *>(tw2s + 16 * 15);        // [1920]
     const int tid = threadIdx.x;
     for (int i = tid; i < 512; i += kStft1920Threads) logtab8[i] = __ldg(&a.logtab[i >> 3]);
-#ifdef FT8B_STFT_LOG1
-    for (int i = tid; i < 64; i += kStft1920Threads) logtab8[i] = __ldg(&a.logtab[i]);
-    const double2 *logtab = logtab8;
-#else
     const double2 *logtab = logtab8 + (tid & 7);                  // this lane's copy
-#endif
     for (int i = tid; i < 16 * 15; i += kStft1920Threads) tw2s[i] = __ldg(&a.tw2[i]);
     const int64_t n_items = a.n_slots * a.frames_out;
     const int Fout = a.bin_hi - a.bin_lo;
@@ -261,7 +250,6 @@ __global__ void __launch_bounds__(kStft1920Threads, MB) stft1920_kernel(const St
     // Each thread copies exactly the sample pairs it will consume in P1 (n = tid + 128 t), so waiting on its own
     // cp.async groups is enough - no block barrier guards the staging buffer.
     auto stage_audio = [&](int64_t it) {
-#ifndef FT8B_STFT_NOSTAGE
         if (VEC && it < n_items) {
             constexpr int kPair = 2 * (int)sizeof(WaveT);
             const char *src = reinterpret_cast<const char *>(frame_audio(it));
@@ -272,22 +260,15 @@ __global__ void __launch_bounds__(kStft1920Threads, MB) stft1920_kernel(const St
             }
         }
         __pipeline_commit();
-#endif
     };
     stage_audio(blockIdx.x);
     __syncthreads();
     for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int64_t slot = item / a.frames_out;
         const int64_t fr = item - slot * a.frames_out;
-#ifdef FT8B_STFT_NOSTAGE
-        const WaveT *x = frame_audio(item);
-#else
         const WaveT *x = VEC ? xs : frame_audio(item);
-#endif
         double *out = a.mag + (slot * a.frames_out + fr) * (int64_t)Fout;
-#ifndef FT8B_STFT_NOSTAGE
         if (VEC) __pipeline_wait_prior(0);     // this thread's pairs of this frame have landed
-#endif
         // ---------------- P1: radix 15, inputs z[j + 128 t] = (w x)[2n] + i (w x)[2n+1], zero for n >= 960
         {
             double2 u[15];

@@ -168,8 +168,9 @@ int ft8b_decode_candidates_drift(const double *mag, int64_t n_slots, int T, int 
 
 /*
  * Whole path, decode_ft8_message (ft8_decode.py:288-394) for a batch of equal-length slots:
- * S1 -> S2a -> S2b -> S3 in chunks of `chunk_slots` slots so the float64 spectrogram and score map of a
- * chunk stay L2-resident between kernels.  `workspace` must hold ft8b_decode_workspace_bytes() bytes.
+ * S1 -> S2a -> S2b -> LLR in chunks of `chunk_slots` slots (the float64 spectrogram and score map exist for one
+ * chunk at a time: 4.2 MB per slot at 12 kHz, osr 2x2), then one LDPC/CRC launch over the candidates of the whole
+ * batch.  `workspace` must hold ft8b_decode_workspace_bytes() bytes.
  * Outputs as in ft8b_select_candidates / ft8b_decode_candidates ([n_slots][K]...).
  */
 typedef struct {
