@@ -306,7 +306,7 @@ int ft8b_decode_slots(const void *wave, int wave_dtype, int64_t n_slots, int64_t
         }
         if (rc) return rc;
         {
-            // LLRs of this chunk's candidates while its spectrogram is still in L2; ok/ldpc_errors serve as scratch
+            // LLRs of this chunk's candidates before its spectrogram is overwritten; ok/ldpc_errors serve as scratch
             StageScope t(3, stream);
             rc = extract_llr(mag, nb, (int)g.T, g.F, p->steps_per_symbol, p->bins_per_tone, cand_time + s0 * K,
                              cand_freq + s0 * K, n_cand + s0, K, 1, llr + s0 * K * kLdpcN, ok + s0 * K, ldpc_errors + s0 * K,
