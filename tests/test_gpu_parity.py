@@ -578,3 +578,28 @@ def test_sync_pair_kernel_equals_single_kernel(monkeypatch, b, s, F, T):
     monkeypatch.delenv("FT8B_SYNC_SINGLE")
     assert pair.shape == single.shape and pair.numel() > 0
     assert torch.equal(pair.view(torch.int64), single.view(torch.int64))
+
+
+@pytest.mark.parametrize("fs", list(range(2000, 10500, 500)))
+def test_ft8_standard_rate_sweep(orc, fs):
+    """The reference's demodulator/test_ft8_standard.py:44-92, one point per sample rate: a burst at f0 = 0 in white noise
+    (-10 dB, the top of its sweep) decoded with (2, 2, K=20, min_score=1, 20 iterations).  nfft = 0.32 fs runs through the
+    generic mixed-radix STFT kernel with odd factors 3, 5, 7, 9, 11, 13, 17, 19; everything the reference would return
+    must equal the oracle's result for the same samples, and the transmitted payload must come back."""
+    rng = np.random.default_rng(fs)
+    payload = bytes(rng.integers(0, 256, 10, dtype=np.uint8) & np.array([255] * 9 + [0xF8], dtype=np.uint8))
+    wave = synth.ft8_generator(payload, fs=fs, f0=0, fc=0)
+    noise_power = np.mean(wave ** 2) / (10 ** (-10 / 10))
+    wave = wave + np.sqrt(noise_power) * rng.standard_normal(len(wave))
+    ref_mag = orc.spectrogram_pos(wave, fs, 2, 2)
+    got_mag = gpu_mag(wave, fs, 2, 2)[0].cpu().numpy().T
+    assert got_mag.shape == ref_mag.shape and np.abs(got_mag - ref_mag).max() < SPEC_TOL_DB
+    got = fd.decode_ft8_message(wave_data=wave, sample_rate=fs, bins_per_tone=2, steps_per_symbol=2, max_candidates=20,
+                                min_score=1, max_iterations=20)
+    ref = orc.decode_ft8_message(wave, fs, 2, 2, 20, 1, 20)
+    assert len(got) == len(ref)
+    for (msg, st, t_sec, f_hz, score), r in zip(got, ref):
+        assert bytes(msg.payload) == r[0] and msg.hash == r[1]
+        assert (st.ldpc_errors, st.crc_extracted) == (r[2], r[3])
+        assert t_sec == r[4] and f_hz == r[5] and abs(score - r[6]) < SCORE_TOL
+    assert payload in [bytes(m.payload) for m, *_ in got]
