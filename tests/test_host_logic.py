@@ -172,3 +172,48 @@ def test_generator_mirror_names():
     w = G.ft8_generator(np.frombuffer(synth.C1_PAYLOAD, dtype=np.uint8), 12000, 500, 0)
     bb = G.ft8_modulation_waveform_generator(G.gfsk_modulation_waveform_generator(G.ft8_encode(synth.C1_PAYLOAD), 12000), 12000, 500)
     assert np.array_equal(np.real(bb), w) and np.array_equal(G.ft8_baseband_generator(synth.C1_PAYLOAD, 12000, 500), bb)
+
+
+# ------------------------------------------------------------------------------------------------
+# Opt-in post-processing: parity unpinned, checked by round trips
+# ------------------------------------------------------------------------------------------------
+def test_unpack77_round_trips():
+    from ft8_demodulator_b200 import postprocess as pp
+    cases = [("CQ", "K1ABC", "FN42"), ("K1ABC", "W9XYZ", "-15"), ("W9XYZ", "K1ABC", "R+05"), ("K1ABC", "W9XYZ", "RR73"),
+             ("CQ DX", "G4ABC", "IO91"), ("CQ 123", "PA9XYZ", "JO22"), ("QRZ", "VK3ABC", ""), ("DE", "JA1XYZ", "73"),
+             ("W1AW", "KA1ABC", "RRR"), ("K1ABC/R", "W9XYZ/R", "R EN37")]
+    for a, b, g in cases:
+        p = pp.pack77_standard(a, b, g)
+        assert len(p) == 10 and p[9] & 7 == 0
+        assert pp.unpack77(p) == " ".join(x for x in (a, b, g) if x)
+    assert pp.unpack77(pp.pack77_standard("G4ABC/P", "PA9XYZ", "JO22", i3=2)) == "G4ABC/P PA9XYZ JO22"
+    for text in ["TNX BOB 73 GL", "HELLO WORLD", "A", "1/2+3-4.5?"]:
+        assert pp.unpack77(pp.pack77_free_text(text)) == text
+    # field-level inverses over their whole ranges (sampled)
+    rng = np.random.default_rng(0)
+    for n in rng.integers(pp.NTOKENS + pp.MAX22, pp.NTOKENS + pp.MAX22 + 37 * 36 * 10 * 27 ** 3, 300):
+        call = pp.unpack_c28(int(n))
+        if len(call.replace(" ", "")) == len(call) and not call.startswith("<"):      # no embedded blanks
+            assert pp.unpack_c28(pp.pack_c28(call)) == call
+    for g in range(0, pp.MAXGRID4, 977):
+        assert pp.pack_g15(pp.unpack_g15(g, 0)) == (g, 0)
+    for rpt in range(-30, 50, 7):
+        assert pp.unpack_g15(*pp.pack_g15("%+03d" % rpt)) == "%+03d" % rpt
+    # telemetry and unknown types never raise
+    v = (0x123456789ABCDEF012 << 6) | (5 << 3)
+    assert pp.unpack77(pp.int77_to_payload(v)) == "123456789ABCDEF012"
+    assert isinstance(pp.unpack77(bytes.fromhex("1c3f8a6ae207a1e39450")), str)
+    with pytest.raises(ValueError):
+        pp.unpack77(b"\x00" * 9)
+
+
+def test_dedupe_keeps_first_occurrence():
+    from ft8_demodulator_b200 import postprocess as pp
+    from ft8_demodulator_b200.ft8_demodulator.ftx_types import FT8DecodeStatus, FT8Message
+    mk = lambda pl, s: (FT8Message(payload=bytearray(pl), hash=1), FT8DecodeStatus(0, 1, 1), 0.0, 100.0, s)
+    a, b = pp.pack77_standard("CQ", "K1ABC", "FN42"), pp.pack77_free_text("HELLO")
+    res = [mk(a, 9.0), mk(b, 8.0), mk(a, 7.5), mk(a, 7.0), mk(b, 6.0)]
+    out = pp.dedupe(res)
+    assert [r[4] for r in out] == [9.0, 8.0]
+    assert [x[0] for x in pp.annotate(res)] == ["CQ K1ABC FN42", "HELLO"]
+    assert len(pp.annotate(res, unique=False)) == 5
