@@ -182,22 +182,24 @@ __device__ __forceinline__ double fast_db(double v, const double2 *__restrict__ 
 
 // Untangle the pair (Z[k], Z[M-k]) of the packed transform into dB for bins k and M-k
 // (spectrogram_analyse.py:59-60: 10*log10(1e-12 + |S|), S = |X|^2 / (sum w)^2).
-__device__ __forceinline__ void untangle_pair(double2 z, double2 zr, double2 w, double scale, const double2 *__restrict__ tab,
+__device__ __forceinline__ void untangle_pair(double2 z, double2 zr, double2 w, double scale4, const double2 *__restrict__ tab,
                                               double &d1, double &d2) {
+    // X[k] = E + (-i) w O with E = (z + conj zr)/2, O = (z - conj zr)/2.  The halves are left out here and folded into
+    // scale4 = scale/4: scaling by a power of two commutes with rounding, so the dB values are the same bit for bit.
     const double2 zc = make_double2(zr.x, -zr.y);
-    const double2 e = make_double2(0.5 * (z.x + zc.x), 0.5 * (z.y + zc.y));
+    const double2 e = cadd(z, zc);
     const double2 p = cmul(w, csub(z, zc));
-    const double re1 = e.x + 0.5 * p.y, im1 = e.y - 0.5 * p.x;
-    const double re2 = e.x - 0.5 * p.y, im2 = e.y + 0.5 * p.x;
-    d1 = fast_db(kK[24] + (re1 * re1 + im1 * im1) * scale, tab);
-    d2 = fast_db(kK[24] + (re2 * re2 + im2 * im2) * scale, tab);
+    const double re1 = e.x + p.y, im1 = e.y - p.x;
+    const double re2 = e.x - p.y, im2 = e.y + p.x;
+    d1 = fast_db(kK[24] + (re1 * re1 + im1 * im1) * scale4, tab);
+    d2 = fast_db(kK[24] + (re2 * re2 + im2 * im2) * scale4, tab);
 }
 
 // general form with band crop: stores bins k and M-k when they fall inside [bin_lo, bin_hi)
 __device__ __forceinline__ void emit_pair(double2 z, double2 zr, int k, bool mirror, const Stft1920Args &a, double *out,
                                           const double2 *__restrict__ tab) {
     double d1, d2;
-    untangle_pair(z, zr, __ldg(&a.twpost[k]), a.scale, tab, d1, d2);
+    untangle_pair(z, zr, __ldg(&a.twpost[k]), 0.25 * a.scale, tab, d1, d2);
     const int k2 = kM1920 - k;
     if (k >= a.bin_lo && k < a.bin_hi) out[k - a.bin_lo] = d1;
     if (mirror && k2 >= a.bin_lo && k2 < a.bin_hi) out[k2 - a.bin_lo] = d2;
@@ -242,6 +244,7 @@ __global__ void __launch_bounds__(kStft1920Threads, MB) stft1920_kernel(const St
     for (int i = tid; i < 16 * 15; i += kStft1920Threads) tw2s[i] = __ldg(&a.tw2[i]);
     const int64_t n_items = a.n_slots * a.frames_out;
     const int Fout = a.bin_hi - a.bin_lo;
+    const double scale4 = 0.25 * a.scale;
     const bool full = (a.bin_lo == 0) && (a.bin_hi >= kM1920);   // bins 0..1919 all stored: no per-bin range checks
     auto frame_audio = [&](int64_t it) -> const WaveT * {
         const int64_t sl = it / a.frames_out;
@@ -360,7 +363,7 @@ __global__ void __launch_bounds__(kStft1920Threads, MB) stft1920_kernel(const St
 #pragma unroll
                 for (int t = 0; t < 8; ++t) {
                     double d1, d2;
-                    untangle_pair(u1[t], u2[7 - t], __ldg(twp + 240 * t), a.scale, logtab, d1, d2);
+                    untangle_pair(u1[t], u2[7 - t], __ldg(twp + 240 * t), scale4, logtab, d1, d2);
                     if (t == 0) *m0 = d2; else mt[t * mstep] = d2;
                     p1[240 * t] = d1;
                 }
