@@ -158,6 +158,8 @@ int ft8b_dechirp(const void *in, int in_dtype, int64_t n, double c2, double c3, 
  * [n_slots][nt][nf]: maximum of ft8_sync_score (ft8_decode.py:47-100, evaluated on the shifted cells) over the
  * hypotheses and its index (first maximum; list d = 0 first).  ft8b_select_candidates then runs on best_score, and
  * ft8b_decode_candidates_drift extracts LLRs along each candidate's drift (cand_drift [n_slots][K], bins/symbol).
+ * The hypothesis list is staged in constant memory in stream order: calls carrying DIFFERENT lists must not be in
+ * flight on different streams of one device at the same time (every other entry point is free of such state).
  */
 int ft8b_sync_scores_drift(const double *mag, int64_t n_slots, int T, int F, int time_osr, int freq_osr, int n_hyp,
                            const double *drift_bins_per_symbol, double *best_score, int32_t *best_hyp, void *stream);
