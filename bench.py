@@ -136,6 +136,17 @@ def measured_traffic_per_slot(stage):
         return None
 
 
+def measured_pipe_utilisation(stage):
+    """FP64-pipe / issue-slot / DRAM utilisation of a stage's kernel from the same committed ncu capture (a static
+    figure from profiles/, not a live measurement): what actually bounds these float64 kernels."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        d = json.load(open(p))[stage]
+        return {"fp64_pipe_pct": d["fp64_pipe_pct"], "issue_active_pct": d["issue_active_pct"], "dram_pct": d["dram_pct"]}
+    except Exception:
+        return None
+
+
 def cpu_threads():
     try:
         return len(os.sched_getaffinity(0))
@@ -375,6 +386,7 @@ def main():
                                     "frac": SURVEY_FP32_BYTES[STAGES[dom]] * units[dom] / (sm[dom] * 1e-3) / 1e9 / peak}
                                    if STAGES[dom] in SURVEY_FP32_BYTES else None),
             "avg_launch_ms": sm[dom] / max(sn[dom], 1),
+            "ncu_utilisation": measured_pipe_utilisation(STAGES[dom]),
             "note": "float64 FFT/stencil/BP kernels are bound by the FP64 pipe and shared memory, not HBM (DESIGN.md)"}
 
     line = {
