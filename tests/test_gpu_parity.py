@@ -603,3 +603,33 @@ def test_ft8_standard_rate_sweep(orc, fs):
         assert (st.ldpc_errors, st.crc_extracted) == (r[2], r[3])
         assert t_sec == r[4] and f_hz == r[5] and abs(score - r[6]) < SCORE_TOL
     assert payload in [bytes(m.payload) for m, *_ in got]
+
+
+def test_concurrent_streams_and_threads():
+    """Two host threads, each on its own CUDA stream, decode different batches at the same time (the C ABI promises
+    thread safety for distinct streams: per-device tables behind mutexes, no other shared state)."""
+    import threading
+    d = dev()
+    batches = [np.stack([synth.c3_slot(100 * k + i)[0] for i in range(6)]).astype(np.float32) for k in range(2)]
+    serial = [fd.decode_slots(b, 12000, 2, 2, max_candidates=20, min_score=1, max_iterations=20).arrays for b in batches]
+    out = [None, None]
+    errs = []
+
+    def work(k):
+        try:
+            s = torch.cuda.Stream(device=d)
+            with torch.cuda.stream(s):
+                for _ in range(3):
+                    w = torch.from_numpy(batches[k]).to(d, non_blocking=True)
+                    out[k] = fd.decode_slots(w, 12000, 2, 2, max_candidates=20, min_score=1, max_iterations=20).arrays
+            s.synchronize()
+        except Exception as e:          # surfaced in the main thread below
+            errs.append(e)
+
+    th = [threading.Thread(target=work, args=(k,)) for k in range(2)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs
+    for k in range(2):
+        for f in serial[k].__dataclass_fields__:
+            assert torch.equal(getattr(serial[k], f), getattr(out[k], f)), (k, f)
