@@ -69,15 +69,53 @@ def parse_args():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """SM clock, power and throttle reasons sampled WHILE the timed region runs: NVML every 5 ms from a thread
+    (the timed region of the default run lasts ~0.1 s), `nvidia-smi -lms 200` if NVML cannot be loaded."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    # NVML clocks-event (throttle) reason bits
+    BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+            "hw_power_brake_slowdown": 0x80}
 
     def __init__(self, gpu_index: int):
         self.idx, self.proc, self.lines = gpu_index, None, []
+        self.nvml, self.handle, self.samples, self.stop_flag, self.thread = None, None, [], False, None
+
+    def _nvml_handle(self):
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        try:
+            pr = torch.cuda.get_device_properties(self.idx)
+            bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.idx)
+        return pynvml, h
+
+    def _poll(self):
+        n, h = self.nvml, self.handle
+        mx = n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)
+        while not self.stop_flag:
+            try:
+                try:
+                    rs = n.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    rs = n.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.samples.append((n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM), mx, n.nvmlDeviceGetPowerUsage(h) / 1000.0, rs))
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
+        try:
+            self.nvml, self.handle = self._nvml_handle()
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
@@ -92,6 +130,14 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=1)
+            sm = [x[0] for x in self.samples]
+            reasons = sorted(nm for nm, bit in self.BITS.items() if any(x[3] & bit for x in self.samples))
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(self.samples[0][1]) if sm else None,
+                    "power_w_max": max(x[2] for x in self.samples) if sm else None, "samples": len(sm), "reasons": reasons,
+                    "source": "nvml, 5 ms period, during the timed region"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.25)
@@ -114,7 +160,8 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons),
+                "source": "nvidia-smi -lms 200"}
 
 
 def measured_peak_gbs():
