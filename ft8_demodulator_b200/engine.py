@@ -297,7 +297,7 @@ class SlotDecoder:
         return o
 
 
-def decode_host_batch(waves: torch.Tensor, params: _lib.DecodeParams, piece_slots: int = 512, device=None) -> SlotDecodes:
+def decode_host_batch(waves: torch.Tensor, params: _lib.DecodeParams, piece_slots: int = 128, device=None) -> SlotDecodes:
     """Host [B, N] tensor -> device results, with the H2D copy of piece i+1 overlapping the kernels of
     piece i (two device staging buffers, one copy stream).  Pinned host memory copies asynchronously."""
     dev = device or require_cuda()
