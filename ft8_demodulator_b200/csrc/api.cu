@@ -21,9 +21,10 @@ void set_error(const char *fmt, ...) {
 // implemented in stft.cu / sync.cu / decode.cu
 int stft_db(const void *, int, int64_t, int64_t, int64_t, int, int, int, int, int, int64_t, int64_t, double *, cudaStream_t);
 int release_plans();
-int sync_scores(const double *, int64_t, int, int, int, int, double *, cudaStream_t);
+int sync_tiles_per_slot(int, int, int, int);
+int sync_scores(const double *, int64_t, int, int, int, int, double *, SyncTile *, cudaStream_t);
 int select_candidates(const double *, int64_t, int, int, int, int, double, int32_t *, int32_t *, double *, int32_t *,
-                      int32_t *, cudaStream_t);
+                      int32_t *, const SyncTile *, int, cudaStream_t);
 int decode_candidates(const double *, int64_t, int, int, int, int, const int32_t *, const int32_t *, const int32_t *, int,
                       int, uint8_t *, int32_t *, int32_t *, int32_t *, uint8_t *, double *, uint8_t *, const double *,
                       cudaStream_t);
@@ -175,14 +176,14 @@ int ft8b_stft_db(const void *wave, int wave_dtype, int64_t n_slots, int64_t n_sa
 }
 
 int ft8b_sync_scores(const double *mag, int64_t n_slots, int T, int F, int s, int b, double *scores, void *stream) {
-    return sync_scores(mag, n_slots, T, F, s, b, scores, (cudaStream_t)stream);
+    return sync_scores(mag, n_slots, T, F, s, b, scores, nullptr, (cudaStream_t)stream);
 }
 
 int ft8b_select_candidates(const double *scores, int64_t n_slots, int nt, int nf, int t0, int K, double min_score,
                            int32_t *cand_time, int32_t *cand_freq, double *cand_score, int32_t *n_cand, int32_t *n_pass,
                            void *stream) {
     return select_candidates(scores, n_slots, nt, nf, t0, K, min_score, cand_time, cand_freq, cand_score, n_cand, n_pass,
-                             (cudaStream_t)stream);
+                             nullptr, 0, (cudaStream_t)stream);
 }
 
 int ft8b_decode_candidates(const double *mag, int64_t n_slots, int T, int F, int s, int b, const int32_t *cand_time,
@@ -239,15 +240,31 @@ int ft8b_dechirp(const void *in, int in_dtype, int64_t n, double c2, double c3, 
     return dechirp(in, in_dtype, n, c2, c3, reinterpret_cast<double2 *>(out), (cudaStream_t)stream);
 }
 
+// Chunking of a batch: per-slot workspace (spectrogram + score map + strip summaries of the sync kernel), and chunks of
+// equal size (4096 slots at a 2045-slot limit run as 3 x 1366, not 2045 + 2045 + 6).
+struct ChunkPlan {
+    int64_t per_slot;   // bytes
+    int chunk, n_tiles;
+};
+static ChunkPlan chunk_plan(const ft8b_decode_params *p, const Geometry &g, int64_t n_slots) {
+    ChunkPlan c;
+    c.n_tiles = sync_tiles_per_slot((int)g.T, g.F, p->steps_per_symbol, p->bins_per_tone);
+    c.per_slot = 8 * (g.mag_elems + g.score_elems) + (int64_t)sizeof(SyncTile) * c.n_tiles;
+    const int64_t n = n_slots > 0 ? n_slots : 1;
+    int64_t lim = p->chunk_slots > 0 ? p->chunk_slots : default_chunk_slots(c.per_slot);
+    if (lim > n) lim = n;
+    const int64_t n_chunks = (n + lim - 1) / lim;
+    c.chunk = (int)((n + n_chunks - 1) / n_chunks);
+    return c;
+}
+
 int64_t ft8b_decode_workspace_bytes(const ft8b_decode_params *p, int64_t n_slots, int64_t n_samples) {
     if (!p) return FT8B_ERR_ARG;
     Geometry g;
     if (geometry(p, n_samples, &g)) return FT8B_ERR_ARG;
-    const int64_t per_slot = 8 * (g.mag_elems + g.score_elems);
-    int chunk = p->chunk_slots > 0 ? p->chunk_slots : default_chunk_slots(per_slot);
-    if (chunk > n_slots) chunk = (int)(n_slots > 0 ? n_slots : 1);
-    // chunk spectrogram + score map, then the LLR vectors of every candidate of the batch
-    return per_slot * chunk + 8ll * kLdpcN * p->max_candidates * (n_slots > 0 ? n_slots : 0) + 256;
+    const ChunkPlan c = chunk_plan(p, g, n_slots);
+    // chunk spectrogram + score map + strip summaries, then the LLR vectors of every candidate of the batch
+    return c.per_slot * c.chunk + 8ll * kLdpcN * p->max_candidates * (n_slots > 0 ? n_slots : 0) + 256;
 }
 
 int ft8b_decode_slots(const void *wave, int wave_dtype, int64_t n_slots, int64_t n_samples, int64_t slot_stride,
@@ -268,7 +285,6 @@ int ft8b_decode_slots(const void *wave, int wave_dtype, int64_t n_slots, int64_t
     if (n_slots <= 0) return 0;
     const int K = p->max_candidates;
     const size_t elt = wave_dtype == FT8B_DTYPE_F32 ? 4 : (wave_dtype == FT8B_DTYPE_I16 ? 2 : 8);
-    const int64_t per_slot = 8 * (g.mag_elems + g.score_elems);
     if (g.T <= 0 || g.F <= 0 || g.score_elems == 0 || K == 0) {
         // nothing to search: the reference returns an empty list
         FT8B_CUDA_TRY(cudaMemsetAsync(n_cand, 0, sizeof(int32_t) * n_slots, stream));
@@ -278,13 +294,15 @@ int ft8b_decode_slots(const void *wave, int wave_dtype, int64_t n_slots, int64_t
         }
         return 0;
     }
-    int chunk = p->chunk_slots > 0 ? p->chunk_slots : default_chunk_slots(per_slot);
-    if (chunk > n_slots) chunk = (int)n_slots;
-    const int64_t need = per_slot * chunk + 8ll * kLdpcN * K * n_slots;
+    const ChunkPlan cp = chunk_plan(p, g, n_slots);
+    const int chunk = cp.chunk;
+    const int64_t need = cp.per_slot * chunk + 8ll * kLdpcN * K * n_slots;
     if (workspace_bytes < need) FT8B_ARG_FAIL("ft8b_decode_slots: workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)need);
     double *mag = reinterpret_cast<double *>(workspace);
     double *scores = mag + g.mag_elems * chunk;
-    double *llr = scores + g.score_elems * chunk;   // [n_slots][K][174]
+    SyncTile *tiles = reinterpret_cast<SyncTile *>(scores + g.score_elems * chunk);   // [chunk][n_tiles], when the sync kernel makes them
+    double *llr = reinterpret_cast<double *>(tiles + (int64_t)cp.n_tiles * chunk);     // [n_slots][K][174]
+    if (cp.n_tiles == 0) tiles = nullptr;
     for (int64_t s0 = 0; s0 < n_slots; s0 += chunk) {
         const int64_t nb = (n_slots - s0 < chunk) ? (n_slots - s0) : chunk;
         const char *w = reinterpret_cast<const char *>(wave) + (size_t)s0 * slot_stride * elt;
@@ -296,13 +314,13 @@ int ft8b_decode_slots(const void *wave, int wave_dtype, int64_t n_slots, int64_t
         if (rc) return rc;
         {
             StageScope t(1, stream);
-            rc = sync_scores(mag, nb, (int)g.T, g.F, p->steps_per_symbol, p->bins_per_tone, scores, stream);
+            rc = sync_scores(mag, nb, (int)g.T, g.F, p->steps_per_symbol, p->bins_per_tone, scores, tiles, stream);
         }
         if (rc) return rc;
         {
             StageScope t(2, stream);
             rc = select_candidates(scores, nb, g.nt, g.nf, g.t0, K, p->min_score, cand_time + s0 * K, cand_freq + s0 * K,
-                                   cand_score + s0 * K, n_cand + s0, nullptr, stream);
+                                   cand_score + s0 * K, n_cand + s0, nullptr, tiles, cp.n_tiles, stream);
         }
         if (rc) return rc;
         {

@@ -26,6 +26,12 @@ constexpr int kLenSync = 7;      // symbols per Costas block
 constexpr int kSyncOffset = 36;  // symbols between Costas block starts
 constexpr int kLdpcN = 174, kLdpcM = 83, kLdpcK = 91;
 
+// arg-max of one warp strip of the score map, written by the sync kernel for the selection (sync_pair.cuh)
+struct SyncTile {
+    double score;
+    long long idx;      // flat scan index (abs_time row * nf + abs_freq); LLONG_MAX when the strip is empty
+};
+
 }  // namespace ft8b
 
 #define FT8B_CUDA_TRY(expr)                                         \

@@ -103,14 +103,51 @@ __device__ __forceinline__ void bf5(double2 &u0, double2 &u1, double2 &u2, doubl
     u3 = cadd(m2, mul_pi(n2));
 }
 
-// 15-point DFT, t = 3a + b in, f = q + 5r out (in place, natural order on both sides)
+// 5-point DFT whose inputs u3 = u4 = 0 / u2 = u3 = u4 = 0 (the zero-padded half of the frame): the sums and
+// differences with a zero operand are dropped by hand - the compiler may not fold x + 0.0 (it would turn -0 into +0).
+__device__ __forceinline__ void bf5_in3(double2 &u0, double2 &u1, double2 &u2, double2 &u3, double2 &u4) {
+    const double c1 = kK[1], c2 = kK[2], s1 = kK[3], s2 = kK[4];
+    const double2 a = u0, t1 = u1, t2 = u2;
+    const double2 m1 = make_double2(a.x + c1 * t1.x + c2 * t2.x, a.y + c1 * t1.y + c2 * t2.y);
+    const double2 m2 = make_double2(a.x + c2 * t1.x + c1 * t2.x, a.y + c2 * t1.y + c1 * t2.y);
+    const double2 n1 = make_double2(s1 * t1.x + s2 * t2.x, s1 * t1.y + s2 * t2.y);
+    const double2 n2 = make_double2(s2 * t1.x - s1 * t2.x, s2 * t1.y - s1 * t2.y);
+    u0 = make_double2(a.x + t1.x + t2.x, a.y + t1.y + t2.y);
+    u1 = cadd(m1, mul_mi(n1));
+    u4 = cadd(m1, mul_pi(n1));
+    u2 = cadd(m2, mul_mi(n2));
+    u3 = cadd(m2, mul_pi(n2));
+}
+__device__ __forceinline__ void bf5_in2(double2 &u0, double2 &u1, double2 &u2, double2 &u3, double2 &u4) {
+    const double c1 = kK[1], c2 = kK[2], s1 = kK[3], s2 = kK[4];
+    const double2 a = u0, t1 = u1;
+    const double2 m1 = make_double2(a.x + c1 * t1.x, a.y + c1 * t1.y);
+    const double2 m2 = make_double2(a.x + c2 * t1.x, a.y + c2 * t1.y);
+    const double2 n1 = make_double2(s1 * t1.x, s1 * t1.y);
+    const double2 n2 = make_double2(s2 * t1.x, s2 * t1.y);
+    u0 = cadd(a, t1);
+    u1 = cadd(m1, mul_mi(n1));
+    u4 = cadd(m1, mul_pi(n1));
+    u2 = cadd(m2, mul_mi(n2));
+    u3 = cadd(m2, mul_pi(n2));
+}
+
+// 15-point DFT, t = 3a + b in, f = q + 5r out (in place, natural order on both sides).
+// HALF: inputs x[8..14] are zero (P1 of the zero-padded frame) and are never read.
+template <bool HALF = false>
 __device__ __forceinline__ void bf15(double2 (&x)[15]) {
     // cos/sin(2*pi*m/15)
     const double C1 = kK[5], S1 = kK[6], C2 = kK[7], S2 = kK[8], C3 = kK[1], S3 = kK[3];
     const double C4 = kK[9], S4 = kK[10], C6 = kK[2], S6 = kK[4], C8 = kK[11], S8 = kK[12];
-    bf5(x[0], x[3], x[6], x[9], x[12]);     // b = 0 : Y0[q] in x[3q]
-    bf5(x[1], x[4], x[7], x[10], x[13]);    // b = 1 : Y1[q] in x[3q+1]
-    bf5(x[2], x[5], x[8], x[11], x[14]);    // b = 2 : Y2[q] in x[3q+2]
+    if (HALF) {
+        bf5_in3(x[0], x[3], x[6], x[9], x[12]);
+        bf5_in3(x[1], x[4], x[7], x[10], x[13]);
+        bf5_in2(x[2], x[5], x[8], x[11], x[14]);
+    } else {
+        bf5(x[0], x[3], x[6], x[9], x[12]);     // b = 0 : Y0[q] in x[3q]
+        bf5(x[1], x[4], x[7], x[10], x[13]);    // b = 1 : Y1[q] in x[3q+1]
+        bf5(x[2], x[5], x[8], x[11], x[14]);    // b = 2 : Y2[q] in x[3q+2]
+    }
     x[4] = cmulc(x[4], C1, S1);   x[5] = cmulc(x[5], C2, S2);     // q = 1 : W15^1, W15^2
     x[7] = cmulc(x[7], C2, S2);   x[8] = cmulc(x[8], C4, S4);     // q = 2 : W15^2, W15^4
     x[10] = cmulc(x[10], C3, S3); x[11] = cmulc(x[11], C6, S6);   // q = 3 : W15^3, W15^6
@@ -289,9 +326,7 @@ __global__ void __launch_bounds__(kStft1920Threads, MB) stft1920_kernel(const St
                     u[t] = make_double2(0.0, 0.0);
                 }
             }
-#pragma unroll
-            for (int t = 8; t < 15; ++t) u[t] = make_double2(0.0, 0.0);
-            bf15(u);
+            bf15<true>(u);                     // u[8..14] (the zero padding) are outputs only
             // Barrier here rather than at the end of the loop: warps that finished the previous frame's P3 early
             // have already loaded and transformed their share of this frame; `s` (still read by slower warps in
             // P3) and the audio staging buffer are only touched after everybody has arrived.

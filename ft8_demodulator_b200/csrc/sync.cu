@@ -34,6 +34,7 @@ struct SyncArgs {
     int nb;              // num_blocks = T / s                       (ftx_types.py:31-34)
     int nu;              // candidates per phase = nb - 49 ; nt = nu*s
     int nf;              // F - 7*b                                   (ft8_decode.py:109)
+    SyncTile *tiles;     // [n_slots][s][tiles per phase] strip arg-maxima, or null (pair kernels only)
 };
 
 // number of comparisons ft8_sync_score makes for time index u (any phase): ft8_decode.py:62-94
@@ -263,6 +264,8 @@ struct SelArgs {
     double min_score;
     int32_t *cand_time, *cand_freq, *n_cand, *n_pass;
     double *cand_score;
+    const SyncTile *tiles;  // [n_slots][n_tiles] strip arg-maxima from the sync kernel, or null: phase B scans the map
+    int n_tiles;
 };
 
 __device__ __forceinline__ bool sel_pass(double v, double thr) {
@@ -349,7 +352,44 @@ __global__ void __launch_bounds__(kSelThreads) select_candidates_kernel(const Se
 
     // ---- phase B: running-record replacement over the passers after the K-th ----
     long long n_pass_total = total_pass;
-    if (cut >= 0 && K > 0) {
+    if (cut >= 0 && K > 0 && a.tiles) {
+        // The later record is the first occurrence of the map's maximum whenever that lies beyond the cut; if it lies
+        // before the cut it is already in H as its best element and nothing later is strictly greater.  So the
+        // maximum over the strip summaries decides, and the rest of the map is not read (n_pass is not available).
+        double bs = -INFINITY;
+        long long bi = 0x7fffffffffffffffLL;
+        const SyncTile *tl = a.tiles + slot * a.n_tiles;
+        for (int i = tid; i < a.n_tiles; i += kSelThreads) {
+            const double v = tl[i].score;
+            const long long vi = tl[i].idx;
+            if (sel_better(v, vi, bs, bi)) { bs = v; bi = vi; }
+        }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+            const double os = __shfl_xor_sync(0xffffffffu, bs, d);
+            const long long oi = __shfl_xor_sync(0xffffffffu, bi, d);
+            if (sel_better(os, oi, bs, bi)) { bs = os; bi = oi; }
+        }
+        if (lane == 0) { red_s[wid] = bs; red_i[wid] = bi; }
+        __syncthreads();
+        if (wid == 0) {
+            bs = red_s[lane]; bi = red_i[lane];
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) {
+                const double os = __shfl_xor_sync(0xffffffffu, bs, d);
+                const long long oi = __shfl_xor_sync(0xffffffffu, bi, d);
+                if (sel_better(os, oi, bs, bi)) { bs = os; bi = oi; }
+            }
+            if (lane == 0 && bi > cut && sel_pass(bs, a.min_score)) {
+                int best = 0;
+                for (int i = 1; i < n_first; ++i)
+                    if (sel_better(hs[i], hi[i], hs[best], hi[best])) best = i;
+                if (bs > hs[best]) { hs[best] = bs; hi[best] = bi; }
+            }
+        }
+        __syncthreads();
+        n_pass_total = -1;
+    } else if (cut >= 0 && K > 0) {
         double bs = -INFINITY;
         long long bi = 0x7fffffffffffffffLL;
         long long extra = 0;
@@ -428,7 +468,20 @@ __global__ void __launch_bounds__(kSelThreads) select_candidates_kernel(const Se
 }
 
 // ------------------------------------------------------------------------------------------
-int sync_scores(const double *mag, int64_t n_slots, int T, int F, int s, int b, double *scores, cudaStream_t stream) {
+// strips per slot the pair kernels summarise (0 when the geometry runs on sync_scores_kernel, which does not)
+int sync_tiles_per_slot(int T, int F, int s, int b) {
+    int t0, nt, nf;
+    ft8b_search_ranges(T, F, s, b, &t0, &nt, &nf);
+    const char *env_single = getenv("FT8B_SYNC_SINGLE");
+    const char *env_scan = getenv("FT8B_SELECT_FULLSCAN");     // "1": A/B switch, the selection scans the whole score map
+    if (nt <= 0 || nf <= 0 || !(b == 1 || b == 2 || b == 4) || (env_single && env_single[0] == '1') ||
+        (env_scan && env_scan[0] == '1'))
+        return 0;
+    return s * ((nf + kPairCols - 1) / kPairCols) * (kPairThreads / 32);
+}
+
+int sync_scores(const double *mag, int64_t n_slots, int T, int F, int s, int b, double *scores, SyncTile *tiles,
+                cudaStream_t stream) {
     if (!mag || !scores) FT8B_ARG_FAIL("ft8b_sync_scores: null pointer");
     if (T < 0 || F < 0 || s < 1 || b < 1) FT8B_ARG_FAIL("ft8b_sync_scores: bad shape");
     int t0, nt, nf;
@@ -437,6 +490,7 @@ int sync_scores(const double *mag, int64_t n_slots, int T, int F, int s, int b, 
     SyncArgs a;
     a.mag = mag; a.scores = scores; a.T = T; a.F = F; a.s = s; a.b = b;
     a.nb = T / s; a.nu = nt / s; a.nf = nf;
+    a.tiles = tiles;
     int dev = 0, max_smem = 0;
     FT8B_CUDA_TRY(cudaGetDevice(&dev));
     FT8B_CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
@@ -462,11 +516,20 @@ int sync_scores(const double *mag, int64_t n_slots, int T, int F, int s, int b, 
     } while (0)
     if (pair) {
         switch (b) {
-            case 1: FT8B_SYNC_LAUNCH(sync_scores_pair_kernel<1>, kPairThreads, kPairCols); break;
-            case 2: FT8B_SYNC_LAUNCH(sync_scores_pair_kernel<2>, kPairThreads, kPairCols); break;
-            default: FT8B_SYNC_LAUNCH(sync_scores_pair_kernel<4>, kPairThreads, kPairCols); break;
+#define FT8B_PAIR_LAUNCH(BB)                                                                                          \
+    do {                                                                                                             \
+        auto kt = sync_scores_pair_kernel<BB, true>;                                                                 \
+        auto kf = sync_scores_pair_kernel<BB, false>;                                                                \
+        auto kern = tiles ? kt : kf;                                                                                 \
+        FT8B_SYNC_LAUNCH(kern, kPairThreads, kPairCols);                                                             \
+    } while (0)
+            case 1: FT8B_PAIR_LAUNCH(1); break;
+            case 2: FT8B_PAIR_LAUNCH(2); break;
+            default: FT8B_PAIR_LAUNCH(4); break;
+#undef FT8B_PAIR_LAUNCH
         }
     } else {
+        if (tiles) FT8B_ARG_FAIL("sync_scores: strip summaries are only produced by the pair kernels");
         switch (b) {       // freq_osr as a compile-time constant turns the 8 tone offsets into immediates
             case 1: FT8B_SYNC_LAUNCH(sync_scores_kernel<1>, kSyncThreads, kSyncThreads); break;
             case 2: FT8B_SYNC_LAUNCH(sync_scores_kernel<2>, kSyncThreads, kSyncThreads); break;
@@ -481,7 +544,8 @@ int sync_scores(const double *mag, int64_t n_slots, int T, int F, int s, int b, 
 
 int select_candidates(const double *scores, int64_t n_slots, int nt, int nf, int t0, int K, double min_score,
                       int32_t *cand_time, int32_t *cand_freq, double *cand_score, int32_t *n_cand, int32_t *n_pass,
-                      cudaStream_t stream) {
+                      const SyncTile *tiles, int n_tiles, cudaStream_t stream) {
+    if (tiles && n_pass) FT8B_ARG_FAIL("select_candidates: n_pass needs the full scan (no strip summaries)");
     if (!cand_time || !cand_freq || !cand_score || !n_cand) FT8B_ARG_FAIL("ft8b_select_candidates: null pointer");
     if (K < 0 || K > FT8B_MAX_CANDIDATES) {
         set_error("ft8b_select_candidates: K=%d outside [0,%d]", K, FT8B_MAX_CANDIDATES);
@@ -501,6 +565,7 @@ int select_candidates(const double *scores, int64_t n_slots, int nt, int nf, int
     a.Kpad = kp;
     a.min_score = min_score;
     a.cand_time = cand_time; a.cand_freq = cand_freq; a.cand_score = cand_score; a.n_cand = n_cand; a.n_pass = n_pass;
+    a.tiles = tiles; a.n_tiles = n_tiles;
     const size_t smem = (size_t)kp * (sizeof(double) + sizeof(long long));
     FT8B_CUDA_TRY(cudaFuncSetAttribute(select_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem > 48 * 1024 ? (int)smem : 48 * 1024));
     select_candidates_kernel<<<(unsigned)n_slots, kSelThreads, smem, stream>>>(a);

@@ -95,7 +95,10 @@ __device__ __forceinline__ void sync_pair_scatter(double *sp, int g, int nu, dou
     }
 }
 
-template <int B>
+// TRACK: every warp also leaves the arg-max of its 64-frequency strip (score, flat scan index; first occurrence
+// in scan order on ties) in a.tiles[slot][rho][warp], so that the selection does not have to re-read the score map
+// to find the running record of ft8_decode.py:134-137 (select_candidates_kernel, phase B).
+template <int B, bool TRACK>
 __global__ void __launch_bounds__(kPairThreads) sync_scores_pair_kernel(const SyncArgs a) {
     using G = PairGeom<B>;
     extern __shared__ double sc[];   // [nu][128] score sums | ring[2 warps][kPairStages][kCol] | double2 ncmp[nu]
@@ -115,7 +118,13 @@ __global__ void __launch_bounds__(kPairThreads) sync_scores_pair_kernel(const Sy
     for (int u = 0; u < nu; ++u) { scp[u * kPairCols] = 0.0; scp[u * kPairCols + 32] = 0.0; }
     __syncthreads();
     const int f_warp = (blockIdx.x * (kPairThreads / 32) + wid) * 64;
-    if (f_warp >= a.nf) return;
+    SyncTile *const tile = TRACK ? a.tiles + (slot * s + rho) * (int64_t)(gridDim.x * (kPairThreads / 32)) +
+                                       blockIdx.x * (kPairThreads / 32) + wid
+                                 : nullptr;
+    if (f_warp >= a.nf) {
+        if (TRACK && lane == 0) { tile->score = -INFINITY; tile->idx = 0x7fffffffffffffffLL; }
+        return;
+    }
     const int base = (lane / B) * 2 * B + lane % B;      // fa - f_warp
     const int fa = f_warp + base, fb = fa + B;
     const int last = nb - 1;
@@ -222,6 +231,8 @@ __global__ void __launch_bounds__(kPairThreads) sync_scores_pair_kernel(const Sy
     double *oa = a.scores + slot * (int64_t)(nu * s) * a.nf + (int64_t)rho * a.nf + (va ? fa : f_warp);
     double *ob = oa + (vb ? fb : f_warp) - (va ? fa : f_warp);
     const int64_t outstep = (int64_t)s * a.nf;
+    double best = -INFINITY;
+    int best_u2 = 0x7fffffff;        // 2u + (0 for fa, 1 for fb) of the first maximum: ascending = scan order within the thread
 #pragma unroll 4
     for (int u = 0; u < nu; ++u) {
         const double2 nr = ncmp[u];
@@ -230,6 +241,26 @@ __global__ void __launch_bounds__(kPairThreads) sync_scores_pair_kernel(const Sy
         if (vb) *ob = yb;
         oa += outstep;
         ob += outstep;
+        if (TRACK) {
+            const bool ga = va & (ya > best);
+            best = ga ? ya : best;
+            best_u2 = ga ? 2 * u : best_u2;
+            const bool gb = vb & (yb > best);
+            best = gb ? yb : best;
+            best_u2 = gb ? 2 * u + 1 : best_u2;
+        }
+    }
+    if (TRACK) {
+        long long bi = 0x7fffffffffffffffLL;
+        if (best_u2 != 0x7fffffff)
+            bi = ((long long)(best_u2 >> 1) * s + rho) * a.nf + ((best_u2 & 1) ? fb : fa);
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+            const double os = __shfl_xor_sync(0xffffffffu, best, d);
+            const long long oi = __shfl_xor_sync(0xffffffffu, bi, d);
+            if (os > best || (os == best && oi < bi)) { best = os; bi = oi; }
+        }
+        if (lane == 0) { tile->score = best; tile->idx = bi; }
     }
 }
 

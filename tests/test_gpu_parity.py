@@ -580,6 +580,32 @@ def test_sync_pair_kernel_equals_single_kernel(monkeypatch, b, s, F, T):
     assert torch.equal(pair.view(torch.int64), single.view(torch.int64))
 
 
+@pytest.mark.parametrize("K,thr", [(20, 1.0), (20, 4.0), (3, -5.0), (1, 1.0), (64, 2.5), (20, 50.0)])
+def test_strip_summaries_equal_full_scan(monkeypatch, K, thr):
+    """ft8b_decode_slots lets the sync kernel leave one arg-max per 64-frequency strip and the selection reads those
+    instead of re-scanning the score map for the later record (ft8_decode.py:134-137).  Same records as the full scan,
+    on noise slots (record far behind the K-th passer), on a slot whose record sits inside the first K passers, on exact
+    ties of the maximum and on a threshold nothing passes."""
+    rng = np.random.default_rng(K)
+    slots = [synth.c3_slot(900 + i)[0] for i in range(4)]
+    slots.append(rng.standard_normal(180000) * 0.1)                       # noise only
+    strong = np.zeros(180000)
+    w = synth.ft8_generator(synth.C1_PAYLOAD, fs=12000, f0=6.25, fc=0)     # record in the very first scan rows
+    strong[:len(w) - 6000] = w[6000:]
+    slots.append(strong + 1e-3 * rng.standard_normal(180000))
+    slots.append(np.zeros(180000))                                        # constant spectrogram: every score ties
+    waves = np.stack(slots).astype(np.float32)
+    kw = dict(max_candidates=K, min_score=thr, max_iterations=5)
+    fused = fd.decode_slots(waves, 12000, 2, 2, **kw).arrays
+    monkeypatch.setenv("FT8B_SELECT_FULLSCAN", "1")
+    scan = fd.decode_slots(waves, 12000, 2, 2, **kw).arrays
+    monkeypatch.delenv("FT8B_SELECT_FULLSCAN")
+    for f in fused.__dataclass_fields__:
+        assert torch.equal(getattr(fused, f), getattr(scan, f)), f
+    if thr < 10:
+        assert int(fused.n_cand[:4].min()) == K
+
+
 @pytest.mark.parametrize("fs", list(range(2000, 10500, 500)))
 def test_ft8_standard_rate_sweep(orc, fs):
     """The reference's demodulator/test_ft8_standard.py:44-92, one point per sample rate: a burst at f0 = 0 in white noise
