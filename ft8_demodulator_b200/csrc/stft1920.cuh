@@ -222,20 +222,25 @@ __device__ __forceinline__ void untangle_pair(double2 z, double2 zr, double2 w, 
                                               double &d1, double &d2) {
     // X[k] = E + (-i) w O with E = (z + conj zr)/2, O = (z - conj zr)/2.  The halves are left out here and folded into
     // scale4 = scale/4: scaling by a power of two commutes with rounding, so the dB values are the same bit for bit.
+    // The contractions are spelled out so that the full-band and the cropped store paths (two inlined copies of this
+    // code) round the same way: their outputs are compared bit for bit.
     const double2 zc = make_double2(zr.x, -zr.y);
     const double2 e = cadd(z, zc);
-    const double2 p = cmul(w, csub(z, zc));
+    const double2 d = csub(z, zc);
+    const double2 p = make_double2(fma(w.x, d.x, -__dmul_rn(w.y, d.y)), fma(w.x, d.y, __dmul_rn(w.y, d.x)));
     const double re1 = e.x + p.y, im1 = e.y - p.x;
     const double re2 = e.x - p.y, im2 = e.y + p.x;
-    d1 = fast_db(kK[24] + (re1 * re1 + im1 * im1) * scale4, tab);
-    d2 = fast_db(kK[24] + (re2 * re2 + im2 * im2) * scale4, tab);
+    d1 = fast_db(fma(fma(re1, re1, __dmul_rn(im1, im1)), scale4, kK[24]), tab);
+    d2 = fast_db(fma(fma(re2, re2, __dmul_rn(im2, im2)), scale4, kK[24]), tab);
 }
 
 // general form with band crop: stores bins k and M-k when they fall inside [bin_lo, bin_hi)
 __device__ __forceinline__ void emit_pair(double2 z, double2 zr, int k, bool mirror, const Stft1920Args &a, double *out,
                                           const double2 *__restrict__ tab) {
     double d1, d2;
-    untangle_pair(z, zr, __ldg(&a.twpost[k]), 0.25 * a.scale, tab, d1, d2);
+    // post-twiddle of k >= 960 as -i W3840^(k - 960), exactly as the full-band path forms it (same bits on both paths)
+    const double2 w0 = __ldg(&a.twpost[k >= 960 ? k - 960 : k]);
+    untangle_pair(z, zr, k >= 960 ? mul_mi(w0) : w0, 0.25 * a.scale, tab, d1, d2);
     const int k2 = kM1920 - k;
     if (k >= a.bin_lo && k < a.bin_hi) out[k - a.bin_lo] = d1;
     if (mirror && k2 >= a.bin_lo && k2 < a.bin_hi) out[k2 - a.bin_lo] = d2;
@@ -360,27 +365,27 @@ __global__ void __launch_bounds__(kStft1920Threads, MB) stft1920_kernel(const St
         }
         __syncthreads();
         // ---------------- P3: radix 8, Ns = 240, paired butterflies + untangling + dB store
-        // Thread i in 0..118 owns butterflies (i+1, 239-i): outputs u1[t] = Z[k], k = i+1 + 240 t, and u2[7-t] = Z[M-k].
+        // Thread i in 0..118 owns butterflies (i+1, 239-i): outputs u1[t] = Z[k], k = i+1 + 240 t, and Z[M-k] from the
+        // second.  Its twiddles are W^(t (240 - j1)) = W8^t conj(W^(t j1)): the conjugates of the first butterfly's
+        // (one table load serves both, and only columns 0..120 of tw3 are ever touched), while the factor W8^t just
+        // rotates the radix-8 outputs by one - so Z[M-k] = u2[(8-t) & 7] with no arithmetic for it.
         // Butterflies 0 and 120 pair with themselves (Z[240 t] with Z[240 ((8-t) & 7)], Z[120 + 240 t] with
-        // Z[120 + 240 (7-t)]).  Threads 119 and 120 run them through the very same instruction stream:
-        //   thread 120: both operands are butterfly 120, u2[7-t] is already the partner;
-        //   thread 119: both are butterfly 0, the second with twiddle column 240 (W8^t), which rotates its outputs
-        //               by one so that u2[7-t] = Z[240 ((8-t) & 7)].
-        // Each of them produces all 8 bins of its butterfly as the "k" output; of the mirrored outputs only the
-        // Nyquist bin (M - 0) is stored.
+        // Z[120 + 240 (7-t)]) and obey the same formulas with j1 = 0 / 120, so threads 119 and 120 run them through the
+        // very same instruction stream.  Each of them produces all 8 bins of its butterfly as the "k" output; of the
+        // mirrored outputs only the Nyquist bin (M - 0) is stored.
         if (tid <= 120) {
             double2 u1[8], u2[8];
             const bool mirror = tid < 119;                                     // the M-k outputs are ours to store
             const bool nyquist = tid == 119 && a.bin_hi > kM1920;              // ... or just bin M
             const int j1 = mirror ? tid + 1 : (tid == 119 ? 0 : 120);
-            const int j2 = mirror ? 239 - tid : j1;                            // row of `s`
-            const int jw2 = (tid == 119) ? 240 : j2;                           // column of tw3
+            const int j2 = (tid == 119) ? 0 : 240 - j1;                        // row of `s` of the second butterfly
 #pragma unroll
             for (int t = 0; t < 8; ++t) { u1[t] = s[j1 + 240 * t]; u2[t] = s[j2 + 240 * t]; }
 #pragma unroll
             for (int t = 1; t < 8; ++t) {
-                u1[t] = cmul(u1[t], __ldg(&a.tw3[t * kTw3Stride + j1]));
-                u2[t] = cmul(u2[t], __ldg(&a.tw3[t * kTw3Stride + jw2]));
+                const double2 w = __ldg(&a.tw3[t * kTw3Stride + j1]);
+                u1[t] = cmul(u1[t], w);
+                u2[t] = cmul(u2[t], make_double2(w.x, -w.y));
             }
             bf8(u1);
             bf8(u2);
@@ -395,15 +400,21 @@ __global__ void __launch_bounds__(kStft1920Threads, MB) stft1920_kernel(const St
                 double *const m0 = (mirror || nyquist) ? p2 : p1, *const mt = mirror ? p2 : p1;
                 const int mstep = mirror ? -240 : 240;
 #pragma unroll
-                for (int t = 0; t < 8; ++t) {
-                    double d1, d2;
-                    untangle_pair(u1[t], u2[7 - t], __ldg(twp + 240 * t), scale4, logtab, d1, d2);
-                    if (t == 0) *m0 = d2; else mt[t * mstep] = d2;
-                    p1[240 * t] = d1;
+                for (int h = 0; h < 4; ++h) {
+                    // W3840^(k + 960) = -i W3840^k: bins k = j1 + 240 h and k + 960 share one post-twiddle load
+                    const double2 w = __ldg(twp + 240 * h);
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const int t = h + 4 * q;
+                        double d1, d2;
+                        untangle_pair(u1[t], u2[(8 - t) & 7], q ? mul_mi(w) : w, scale4, logtab, d1, d2);
+                        if (t == 0) *m0 = d2; else mt[t * mstep] = d2;
+                        p1[240 * t] = d1;
+                    }
                 }
             } else {
 #pragma unroll
-                for (int t = 0; t < 8; ++t) emit_pair(u1[t], u2[7 - t], j1 + 240 * t, mirror || (t == 0 && nyquist), a, out, logtab);
+                for (int t = 0; t < 8; ++t) emit_pair(u1[t], u2[(8 - t) & 7], j1 + 240 * t, mirror || (t == 0 && nyquist), a, out, logtab);
             }
         }
     }

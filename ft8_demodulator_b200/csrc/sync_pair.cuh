@@ -129,15 +129,19 @@ __global__ void __launch_bounds__(kPairThreads) sync_scores_pair_kernel(const Sy
     const int fa = f_warp + base, fb = fa + B;
     const int last = nb - 1;
 
-    // ---- staging: lane copies strip bins lane, lane+32, lane+64 of a column into their swizzled ring positions.
+    // ---- staging: lane copies strip bins sb, sb+32, sb+64 of a column into their swizzled ring positions.
     // Every lane always issues its three 8-byte cp.async; a copy that has no source (beyond the strip, the row or the
     // last column) is issued with 0 source bytes (nothing is read, zeros are written) - no branch, no divergence.
     const double *col0 = a.mag + slot * (int64_t)a.T * a.F + (int64_t)rho * a.F + f_warp;
     const int64_t rowstep = (int64_t)s * a.F;
     const int f_room = a.F - f_warp;
-    const bool c0 = lane < f_room, c1 = lane + 32 < f_room, c2 = (lane + 64 < G::kStrip) && (lane + 64 < f_room);
-    const int d0 = G::pos(lane), d1 = G::pos(lane + 32), d2o = G::pos(lane + 64);
-    const double *src = col0 + lane;                     // this lane's first bin of the next column to stage
+    // Which bin a lane stages: the swizzle that makes the tone reads conflict-free puts bins i and i + 2 (B = 2) of a
+    // column into the same bank, so lanes staging consecutive bins would write with 2-way conflicts.  Each half-warp
+    // takes the bins with the same (i / B) parity instead: 16 different 8-byte banks per wavefront again.
+    const int sb = ((lane & 15) / B) * 2 * B + (lane >> 4) * B + (lane & 15) % B;
+    const bool c0 = sb < f_room, c1 = sb + 32 < f_room, c2 = (sb + 64 < G::kStrip) && (sb + 64 < f_room);
+    const int d0 = G::pos(sb), d1 = G::pos(sb + 32), d2o = G::pos(sb + 64);
+    const double *src = col0 + sb;                       // this lane's first bin of the next column to stage
     double *wr = ring;                                   // ring slot of the next column to stage
     int staged = 0;                                      // next column to stage
     const int z0 = c0 ? 0 : 8, z1 = c1 ? 0 : 8, z2 = c2 ? 0 : 8;      // source bytes to skip (8 = copy nothing)
