@@ -46,7 +46,9 @@ WORKLOAD = ("C3: batch of %d independent synthetic 15-s FT8 slots per GPU, 12 kH
 # algorithmic bytes per unit (float64 spectrogram as computed here; stated in DESIGN.md)
 STFT_BYTES_PER_SLOT = 180000 * 4 + 1920 * 186 * 8      # read audio f32 + write dB f64
 SYNC_BYTES_PER_SLOT = 1920 * 186 * 8 + 88 * 1906 * 8   # read dB f64 + write score map f64
-SELECT_BYTES_PER_SLOT = 88 * 1906 * 8
+# the selection reads the head of the score map until K passers are found (one 4096-score pass here: min_score = 1 is
+# passed at once) plus the 60 strip arg-maxima the sync kernel leaves; it no longer re-reads the map
+SELECT_BYTES_PER_SLOT = 4096 * 8 + 60 * 16
 LDPC_BYTES_PER_WORD = 174 * 8 + 10 + 1 + 3 * 4
 # SURVEY.md 8d quotes the same stages for a float32 spectrogram (a design this repo rejects);
 # reported next to the float64 figures so both readings of the contract are on the line
@@ -257,6 +259,7 @@ def main():
     if world != args.gpus and world > 1:
         args.gpus = world
     torch.cuda.set_device(local_rank)
+    numa = fdist.bind_host_to_gpu_numa(local_rank)      # before any pinned buffer exists
     dev = torch.device("cuda", local_rank)
     L = _lib.lib()
     B = args.slots
@@ -324,19 +327,25 @@ def main():
         for _ in range(2):
             res = fd.decode_slots(host, FS, chunk_slots=args.chunk, **kw)
         barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
+        ev0.record()
         e2e_steps = max(2, min(args.steps, 3))
         for _ in range(e2e_steps):
             res = fd.decode_slots(host, FS, chunk_slots=args.chunk, **kw)
+        ev1.record()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
+        dt_dev = ev0.elapsed_time(ev1) * 1e-3
         if world > 1:
-            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            t = torch.tensor([dt, dt_dev], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
+            dt, dt_dev = float(t[0].item()), float(t[1].item())
         same = all(torch.equal(getattr(res.arrays, f), getattr(out, f)) for f in out.__dataclass_fields__)
         e2e = {"value": world * B * e2e_steps / dt, "unit": "slots/s", "h2d_bytes_per_step": int(host.numel() * 4),
                "d2h_bytes_per_step": int(res.arrays.nbytes()), "ms_per_step": 1e3 * dt / e2e_steps,
+               "timing": "host wall clock around the calls (results are host arrays when a call returns), max over ranks",
+               "cuda_event_ms_per_step": 1e3 * dt_dev / e2e_steps,
                "identical_to_device_resident_run": bool(same)}
         del host
         # same call fed 16-bit PCM (what a WAV file / SDR capture holds; from_wave.py semantics): half the PCIe bytes.
@@ -445,7 +454,7 @@ def main():
         "candidates_per_s": value * 88 * 1906, "ldpc_codewords_per_s": world * n_words / (ms_step * 1e-3),
         "roofline": roof, "stages": stages, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
         "clocks": clocks, "decode_check": {"slots_with_tx_payload_decoded": hit, "slots": B}, "parity": parity,
-        "gather_ms": gather_ms,
+        "gather_ms": gather_ms, "host_numa_binding": numa,
     }
     print(json.dumps(line))
     if world > 1:

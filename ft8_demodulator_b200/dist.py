@@ -26,6 +26,53 @@ def env_rank_world() -> Tuple[int, int, int]:
             int(os.environ.get("WORLD_SIZE", "1")))
 
 
+def _parse_cpulist(text: str):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_host_to_gpu_numa(device_index: int, sysfs: str = "/sys") -> dict:
+    """Pin this process to the CPUs of the NUMA node the GPU hangs off, BEFORE its pinned staging buffers are
+    allocated (first touch then places them on that node).  With one process per GPU this keeps every rank's
+    host->device stream on its own socket's memory controllers instead of crossing the inter-socket link, which is
+    what bounds the end-to-end rate once several GPUs ingest audio at PCIe speed.  Best effort: returns what was done
+    ({"node": n, "cpus": k}) or why nothing was ({"skipped": reason}); FT8B_NUMA_BIND=0 disables it."""
+    if os.environ.get("FT8B_NUMA_BIND", "1") == "0":
+        return {"skipped": "FT8B_NUMA_BIND=0"}
+    try:
+        pr = torch.cuda.get_device_properties(device_index)
+        if all(isinstance(getattr(pr, k, None), int) for k in ("pci_domain_id", "pci_bus_id", "pci_device_id")):
+            bus = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        else:
+            import pynvml
+            pynvml.nvmlInit()
+            uuid = str(pr.uuid)
+            h = pynvml.nvmlDeviceGetHandleByUUID((uuid if uuid.startswith("GPU-") else "GPU-" + uuid).encode())
+            bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+            bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+            if len(bus.split(":")[0]) == 8:          # NVML prints an 8-digit domain, sysfs uses 4
+                bus = bus[4:]
+        with open(f"{sysfs}/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return {"skipped": "no NUMA affinity reported for " + bus}
+        with open(f"{sysfs}/devices/system/node/node{node}/cpulist") as f:
+            cpus = _parse_cpulist(f.read())
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        if not use:
+            return {"skipped": f"node {node} has no CPU this process may run on"}
+        os.sched_setaffinity(0, use)
+        return {"node": node, "cpus": len(use), "pci": bus}
+    except Exception as e:                        # containers without sysfs/NVML: leave the scheduler alone
+        return {"skipped": f"{type(e).__name__}: {e}"}
+
+
 def init_process_group(backend: str = None) -> Tuple[int, int, int]:
     rank, local_rank, world = env_rank_world()
     if world > 1 and not dist.is_initialized():
@@ -35,6 +82,7 @@ def init_process_group(backend: str = None) -> Tuple[int, int, int]:
         os.environ.setdefault("MASTER_PORT", "29500")
         if backend == "nccl":
             torch.cuda.set_device(local_rank)
+            bind_host_to_gpu_numa(local_rank)
         dist.init_process_group(backend=backend, rank=rank, world_size=world)
     return rank, local_rank, world
 

@@ -129,6 +129,17 @@ def test_gather_records_world2_gloo():
     mp.spawn(_gather_worker, args=(2, _free_port(), 11, 4), nprocs=2, join=True)
 
 
+def test_numa_binding_helpers(monkeypatch):
+    assert fdist._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert fdist._parse_cpulist("") == set()
+    monkeypatch.setenv("FT8B_NUMA_BIND", "0")
+    assert "skipped" in fdist.bind_host_to_gpu_numa(0)
+    monkeypatch.delenv("FT8B_NUMA_BIND")
+    before = os.sched_getaffinity(0)
+    assert "skipped" in fdist.bind_host_to_gpu_numa(0)        # no CUDA device here: best effort, never raises
+    assert os.sched_getaffinity(0) == before
+
+
 def test_pack_records_layout():
     from ft8_demodulator_b200 import engine
     o = engine.alloc_slot_decodes(2, 3, torch.device("cpu"))
