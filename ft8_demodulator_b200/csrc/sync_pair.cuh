@@ -8,13 +8,17 @@
 // per-step overhead (cp.async staging, waits, score-slot predicates) is paid once per pair.  Every score is still
 // the same sequence of IEEE additions as in sync_scores_kernel, so the two kernels agree bit for bit.
 //
-// Layout.  A warp owns 64 consecutive candidate frequencies; lane l walks fa = f_warp + (l / B) * 2B + l % B and
+// Layout.  A warp owns 64 consecutive candidate frequencies; a lane walks fa = f_warp + PairGeom::lane_base(lane) and
 // fb = fa + B.  CTA = 2 warps = 128 frequencies x one time-oversampling phase x one slot (the score sums,
 // [nu][128] float64 in shared memory, cap the occupancy at 4 CTAs per SM either way).  Each warp streams its
 // (64 + 7B)-bin strip through a private 6-column cp.async ring (two columns per commit group, four in flight) and
-// prefetches the tone bins of column g+2 into registers while it does the arithmetic of step g.  Inside a ring column bin i sits at
-// (i % 2B) * PITCH + i / 2B: for a fixed tone offset the 32 lanes then read 32 different banks (bin order would give
-// a 2-way conflict, the lanes of a pair being 2B bins apart).
+// prefetches the tone bins of column g+2 into registers while it does the arithmetic of step g.  Inside a ring column
+// bin i sits at (i % 2B) * PITCH + i / 2B, with PITCH chosen so that both the staging writes (16 consecutive bins per
+// half-warp) and the tone reads (16 lanes, fixed tone offset) touch 16 different banks.
+// The kernel is bound by the shared-memory/L1 data pipe (ncu: l1tex__data_pipe_lsu_wavefronts 89 % of peak, FP64
+// pipe 45 %), so wavefronts are what is counted here: per warp and column 18 for the tone reads, 5 for staging
+// (12 before the bank fix and before lanes stopped zero-filling positions beyond the strip), ~7 for the score sums
+// (the m = 0 block is stored, not added, and the sums are not zero-filled first: ~10 before).
 #pragma once
 
 namespace ft8b {
@@ -27,13 +31,20 @@ constexpr int kPairStages = 6;       // ring columns per warp, staged two at a t
 template <int B>
 struct PairGeom {
     static constexpr int kStrip = 64 + 7 * B;                               // bins a warp touches per column
-    // plane pitch: >= 96 / 2B so that the 96 staging positions of a column are distinct, and = 8 (B = 2) or 4 (B = 4)
-    // modulo 16 so that the lanes of a half-warp fall into 16 different 8-byte banks
-    static constexpr int kPitch = (B == 1) ? 48 : (B == 2) ? 24 : 20;
+    // plane pitch: >= 96 / 2B so that the 96 staging positions of a column are distinct.  Modulo 16 it is 8 (B = 1) or
+    // 12 (B = 2): 16 consecutive bins - one 128-byte line of the spectrogram, staged by one half-warp - then land in 16
+    // different 8-byte banks, and so do the tone reads of a half-warp (lane_base() below).  ncu: 2.0 instead of 4.0
+    // wavefronts per cp.async on both sides.  B = 4 keeps conflict-free reads only.
+    static constexpr int kPitch = (B == 1) ? 56 : (B == 2) ? 28 : 20;
     static constexpr int kCol = 2 * B * kPitch;                             // doubles per ring column
     __host__ __device__ static constexpr int pos(int i) { return (i % (2 * B)) * kPitch + i / (2 * B); }
     // offset of tone bin tau relative to the lane's base position pos((l / B) * 2B + l % B)
     __host__ __device__ static constexpr int tone(int tau) { return B * (tau & 1) * kPitch + tau / 2; }
+    // fa - f_warp of a lane.  Candidates fa = 2B j + c (c < B) sit at c * kPitch + j: a half-warp takes one c
+    // (B = 2: lanes 0-15 walk fa = 4 l, lanes 16-31 fa = 4 (l - 16) + 1) so that its 16 reads hit 16 banks.
+    __host__ __device__ static constexpr int lane_base(int lane) {
+        return (B == 2) ? (lane & 15) * 4 + (lane >> 4) : (lane / B) * 2 * B + lane % B;
+    }
 };
 
 template <int B>
@@ -83,10 +94,15 @@ __device__ __forceinline__ void sync_pair_step(const double (&cur)[9], const dou
 }
 
 // add the finished block sums S7(h = g-6) of step g into score[u] for u = h+10, h-26, h-62 (m = 0, 1, 2);
-// sp = &score[u = g+4] of fa, fb sits 32 doubles further
+// sp = &score[u = g+4] of fa, fb sits 32 doubles further.  The m = 0 block is the first contribution a score gets
+// (u >= 4; rows 0..3 have no m = 0 block and start from zero), so it is stored, not added: no load, no zero fill.
 __device__ __forceinline__ void sync_pair_scatter(double *sp, int g, int nu, double da, double db) {
+    if ((unsigned)(g + 4) < (unsigned)nu) {
+        sp[0] = da;
+        sp[32] = db;
+    }
 #pragma unroll
-    for (int m = 0; m < 3; ++m) {
+    for (int m = 1; m < 3; ++m) {
         if ((unsigned)(g + 4 - m * kSyncOffset) < (unsigned)nu) {
             double *q = sp - m * kSyncOffset * kPairCols;
             q[0] = __dadd_rn(q[0], da);
@@ -115,7 +131,7 @@ __global__ void __launch_bounds__(kPairThreads) sync_scores_pair_kernel(const Sy
     }
     // score sums of this thread: fa in column wid*64 + lane, fb 32 columns further (both conflict-free)
     double *scp = sc + wid * 64 + lane;
-    for (int u = 0; u < nu; ++u) { scp[u * kPairCols] = 0.0; scp[u * kPairCols + 32] = 0.0; }
+    for (int u = 0; u < nu && u < 4; ++u) { scp[u * kPairCols] = 0.0; scp[u * kPairCols + 32] = 0.0; }   // see sync_pair_scatter
     __syncthreads();
     const int f_warp = (blockIdx.x * (kPairThreads / 32) + wid) * 64;
     SyncTile *const tile = TRACK ? a.tiles + (slot * s + rho) * (int64_t)(gridDim.x * (kPairThreads / 32)) +
@@ -125,35 +141,40 @@ __global__ void __launch_bounds__(kPairThreads) sync_scores_pair_kernel(const Sy
         if (TRACK && lane == 0) { tile->score = -INFINITY; tile->idx = 0x7fffffffffffffffLL; }
         return;
     }
-    const int base = (lane / B) * 2 * B + lane % B;      // fa - f_warp
+    const int base = G::lane_base(lane);                 // fa - f_warp
     const int fa = f_warp + base, fb = fa + B;
     const int last = nb - 1;
 
-    // ---- staging: lane copies strip bins sb, sb+32, sb+64 of a column into their swizzled ring positions.
-    // Every lane always issues its three 8-byte cp.async; a copy that has no source (beyond the strip, the row or the
-    // last column) is issued with 0 source bytes (nothing is read, zeros are written) - no branch, no divergence.
+    // ---- staging: lane copies strip bins lane, lane+32, lane+64 of a column into their swizzled ring positions.
+    // No bounds handling inside the loop: a bin beyond the row (only candidates >= nf, which are never stored, read
+    // it) is replaced by the strip's first bin, and columns beyond the last one (only ever loaded as the unused
+    // successor of the last step) by the last column - every copy has a valid source, so each is ONE cp.async (a
+    // run-time source size compiles to two predicated LDGSTS variants per copy), and the third copy is predicated
+    // off for the lanes the strip has no bin for.
     const double *col0 = a.mag + slot * (int64_t)a.T * a.F + (int64_t)rho * a.F + f_warp;
     const int64_t rowstep = (int64_t)s * a.F;
     const int f_room = a.F - f_warp;
-    // Which bin a lane stages: the swizzle that makes the tone reads conflict-free puts bins i and i + 2 (B = 2) of a
-    // column into the same bank, so lanes staging consecutive bins would write with 2-way conflicts.  Each half-warp
-    // takes the bins with the same (i / B) parity instead: 16 different 8-byte banks per wavefront again.
-    const int sb = ((lane & 15) / B) * 2 * B + (lane >> 4) * B + (lane & 15) % B;
-    const bool c0 = sb < f_room, c1 = sb + 32 < f_room, c2 = (sb + 64 < G::kStrip) && (sb + 64 < f_room);
-    const int d0 = G::pos(sb), d1 = G::pos(sb + 32), d2o = G::pos(sb + 64);
-    const double *src = col0 + sb;                       // this lane's first bin of the next column to stage
-    double *wr = ring;                                   // ring slot of the next column to stage
+    const int has2 = lane + 64 < G::kStrip;              // the strip's bins 64..kStrip-1: the low lanes only
+    const int b0 = lane < f_room ? lane : 0, b1 = lane + 32 < f_room ? lane + 32 : 0,
+              b2 = (has2 && lane + 64 < f_room) ? lane + 64 : 0;
+    const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring);
+    const unsigned d0 = ring_s + 8u * G::pos(lane), d1 = ring_s + 8u * G::pos(lane + 32),
+                   d2o = ring_s + 8u * G::pos(has2 ? lane + 64 : lane);
+    const double *src = col0;                            // first bin of the strip in the next column to stage
+    unsigned wr = 0;                                     // byte offset of the ring slot of the next column to stage
     int staged = 0;                                      // next column to stage
-    const int z0 = c0 ? 0 : 8, z1 = c1 ? 0 : 8, z2 = c2 ? 0 : 8;      // source bytes to skip (8 = copy nothing)
     auto stage_col = [&]() {
-        const bool live = staged <= last;
-        __pipeline_memcpy_async(wr + d0, src, 8, live ? z0 : 8);
-        __pipeline_memcpy_async(wr + d1, src + 32, 8, live ? z1 : 8);
-        __pipeline_memcpy_async(wr + d2o, src + 64, 8, live ? z2 : 8);
-        src += rowstep;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %6, 0;\n\t"
+            "cp.async.ca.shared.global [%0], [%3], 8;\n\t"
+            "cp.async.ca.shared.global [%1], [%4], 8;\n\t"
+            "@p cp.async.ca.shared.global [%2], [%5], 8;\n\t}"
+            :: "r"(d0 + wr), "r"(d1 + wr), "r"(d2o + wr), "l"(src + b0), "l"(src + b1), "l"(src + b2), "r"(has2)
+            : "memory");
+        src += (staged < last) ? rowstep : 0;
         ++staged;
-        wr += G::kCol;
-        if (wr == ring_end) wr = ring;
+        wr += 8u * G::kCol;
+        if (wr == 8u * kPairStages * G::kCol) wr = 0;
     };
     auto stage_two = [&]() { stage_col(); stage_col(); __pipeline_commit(); };
 
