@@ -432,8 +432,9 @@ int stft_db(const void *wave, int wave_dtype, int64_t n_slots, int64_t n_samples
         f.win = plan->win; f.tw2 = plan->tw2; f.tw3 = plan->tw3; f.twpost = plan->twpost; f.logtab = plan->logtab; f.scale = plan->scale;
         f.bin_lo = bin_lo; f.bin_hi = bin_hi; f.frame_lo = frame_lo; f.frames_out = frame_hi - frame_lo; f.mag = mag;
         const int64_t items = n_slots * f.frames_out;
-        // persistent CTAs: 3 per SM x 148 SMs, 8 waves so that the tail of the grid-stride loop stays short
-        constexpr int64_t kGrid1920 = 148 * 3 * 8;
+        // grid-stride CTAs: 3 per SM x 148 SMs x 16 waves (measured per 4096 slots: 1 wave 8.47 ms, 4: 8.12, 8: 8.02,
+        // 16: 7.98, 64: 8.05 - the block scheduler evens out SMs; beyond 16 the per-CTA table staging shows)
+        constexpr int64_t kGrid1920 = 148 * 3 * 16;
         const int64_t g1920 = items < kGrid1920 ? items : kGrid1920;
         // vector loads of sample pairs need every frame start to be 2-element aligned
         // the staged path copies sample pairs with cp.async: every frame start must be pair aligned
