@@ -83,7 +83,8 @@ def init_process_group(backend: str = None) -> Tuple[int, int, int]:
         if backend == "nccl":
             torch.cuda.set_device(local_rank)
             bind_host_to_gpu_numa(local_rank)
-        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+        kw = {"device_id": torch.device("cuda", local_rank)} if backend == "nccl" else {}
+        dist.init_process_group(backend=backend, rank=rank, world_size=world, **kw)
     return rank, local_rank, world
 
 

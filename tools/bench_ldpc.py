@@ -14,6 +14,9 @@ import time
 
 import numpy as np
 
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":     # keep stdout to the one JSON line
+    os.environ["NCCL_DEBUG"] = "WARN"
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "oracle")):
     sys.path.insert(0, p)
