@@ -52,6 +52,7 @@ SIGNATURES = {
     "ft8b_column_argmax": (_i, [_vp, _i64, _i, _i, _i, _vp, _vp]),
     "ft8b_dechirp": (_i, [_vp, _i, _i64, _d, _d, _vp, _vp]),
     "ft8b_sync_scores_drift": (_i, [_vp, _i64, _i, _i, _i, _i, _i, C.POINTER(C.c_double), _vp, _vp, _vp]),
+    "ft8b_sync_scores_drift_direct": (_i, [_vp, _i64, _i, _i, _i, _i, _i, C.POINTER(C.c_double), _vp, _vp, _vp]),
     "ft8b_decode_candidates_drift": (_i, [_vp, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp,
                                           _vp]),
     "ft8b_decode_workspace_bytes": (_i64, [C.POINTER(DecodeParams), _i64, _i64]),

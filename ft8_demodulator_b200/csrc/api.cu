@@ -28,7 +28,7 @@ int select_candidates(const double *, int64_t, int, int, int, int, double, int32
 int decode_candidates(const double *, int64_t, int, int, int, int, const int32_t *, const int32_t *, const int32_t *, int,
                       int, uint8_t *, int32_t *, int32_t *, int32_t *, uint8_t *, double *, uint8_t *, const double *,
                       cudaStream_t);
-int sync_scores_drift(const double *, int64_t, int, int, int, int, int, const double *, double *, int32_t *, cudaStream_t);
+int sync_scores_drift(const double *, int64_t, int, int, int, int, int, const double *, double *, int32_t *, int, cudaStream_t);
 int ldpc_crc(const double *, int64_t, int, uint8_t *, int32_t *, int32_t *, int32_t *, uint8_t *, uint8_t *, cudaStream_t);
 int extract_llr(const double *, int64_t, int, int, int, int, const int32_t *, const int32_t *, const int32_t *, int, int,
                 double *, uint8_t *, int32_t *, cudaStream_t);
@@ -205,7 +205,13 @@ int ft8b_decode_candidates_drift(const double *mag, int64_t n_slots, int T, int 
 
 int ft8b_sync_scores_drift(const double *mag, int64_t n_slots, int T, int F, int s, int b, int n_hyp,
                            const double *drift_bins_per_symbol, double *best_score, int32_t *best_hyp, void *stream) {
-    return sync_scores_drift(mag, n_slots, T, F, s, b, n_hyp, drift_bins_per_symbol, best_score, best_hyp,
+    return sync_scores_drift(mag, n_slots, T, F, s, b, n_hyp, drift_bins_per_symbol, best_score, best_hyp, 0,
+                             (cudaStream_t)stream);
+}
+
+int ft8b_sync_scores_drift_direct(const double *mag, int64_t n_slots, int T, int F, int s, int b, int n_hyp,
+                                  const double *drift_bins_per_symbol, double *best_score, int32_t *best_hyp, void *stream) {
+    return sync_scores_drift(mag, n_slots, T, F, s, b, n_hyp, drift_bins_per_symbol, best_score, best_hyp, 1,
                              (cudaStream_t)stream);
 }
 

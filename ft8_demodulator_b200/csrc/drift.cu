@@ -85,11 +85,18 @@ int dechirp(const void *in, int in_dtype, int64_t n, double c2, double c3, doubl
 // neighbouring bins leave the waterfall are skipped like out-of-range symbols.
 // ------------------------------------------------------------------------------------------------------------
 constexpr int kMaxDriftHyp = 128;
+constexpr int kNumCells = kNumSync * kLenSync;     // 21 Costas cells per candidate
+constexpr int kDriftStrip = 128;                   // candidate frequencies (= threads) per CTA of the tiled kernel
+constexpr int kMaxDriftShift = 64;                 // largest |round(d*q)| the tiled kernel stages; beyond: direct kernel
 __device__ __constant__ double c_drift[kMaxDriftHyp];
+__device__ __constant__ int c_cell_off[kMaxDriftHyp * kNumCells];   // byte offset of (hypothesis, cell) in the CTA's tile
 __device__ __constant__ int c_costas[7] = {3, 1, 4, 0, 6, 5, 2};
 
-__global__ void sync_scores_drift_kernel(const double *mag, int T, int F, int s, int b, int nb, int t0, int nt, int nf,
-                                         int n_hyp, double *best_score, int32_t *best_hyp) {
+// Direct formulation: one thread per (time, frequency), the definition evaluated hypothesis by hypothesis with the
+// reference's running sum.  Any shift magnitude; used for |shift| > kMaxDriftShift and as the cross-check of the
+// tiled kernel (tests/test_gpu_parity.py).
+__global__ void sync_scores_drift_direct_kernel(const double *mag, int T, int F, int s, int b, int nb, int t0, int nt, int nf,
+                                                int n_hyp, double *best_score, int32_t *best_hyp) {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     const int ti = blockIdx.y;
     const int64_t slot = blockIdx.z;
@@ -128,19 +135,175 @@ __global__ void sync_scores_drift_kernel(const double *mag, int T, int F, int s,
     best_hyp[o] = bh;
 }
 
-int sync_scores_drift(const double *mag, int64_t n_slots, int T, int F, int s, int b, int n_hyp,
-                      const double *drift_bins_per_symbol, double *best_score, int32_t *best_hyp, cudaStream_t stream) {
-    if (!mag || !drift_bins_per_symbol || !best_score || !best_hyp) FT8B_ARG_FAIL("ft8b_sync_scores_drift: null pointer");
+// Tiled formulation.  The score of (abs_time, abs_freq, hypothesis) is a sum of 21 cell contrasts
+//   C_q(x) = [p - low] + (p - high) + [p - earlier] + [p - later],   p = mag[abs_time + q*s][x],
+// evaluated at x = abs_freq + tone_q*b + shift(h, q).  C_q(x) does not depend on the hypothesis, only WHERE it is
+// read does, so a CTA (one slot, one abs_time, 128 consecutive abs_freq) first forms the 21 rows of contrasts over
+// the strip widened by the largest shift (5 loads + <= 7 adds per cell, once), and then every thread walks the
+// hypotheses with 21 shared-memory loads and 21 adds each instead of 105 global loads and 168 flops.  The byte offset
+// of (hypothesis, cell) inside the tile comes from constant memory (warp-uniform).  Cells whose symbol or bins fall
+// outside the waterfall contribute 0 and are not counted (same rule as the direct kernel); only the first and last
+// strip can lose cells in frequency, so the per-cell counts exist in the EDGE instantiation only.
+// Summation: contrasts per cell, cells per Costas block, blocks - within 1e-12 of the running sum (test).
+template <bool EDGE>
+__device__ __forceinline__ void drift_walk(const char *tile_thread, const unsigned char *cnt_thread, int n_hyp, int n_time,
+                                           double &best, int &bh) {
+    best = -INFINITY;
+    bh = 0;
+    for (int h = 0; h < n_hyp; ++h) {
+        const int *off = c_cell_off + h * kNumCells;
+        double blk_sum[kNumSync];
+        int n = 0;
+#pragma unroll
+        for (int m = 0; m < kNumSync; ++m) {
+            double a = *reinterpret_cast<const double *>(tile_thread + off[m * kLenSync]);
+            if (EDGE) n += cnt_thread[off[m * kLenSync] >> 3];
+#pragma unroll
+            for (int k = 1; k < kLenSync; ++k) {
+                a = __dadd_rn(a, *reinterpret_cast<const double *>(tile_thread + off[m * kLenSync + k]));
+                if (EDGE) n += cnt_thread[off[m * kLenSync + k] >> 3];
+            }
+            blk_sum[m] = a;
+        }
+        double v = __dadd_rn(__dadd_rn(blk_sum[0], blk_sum[1]), blk_sum[2]);
+        if (EDGE) v = (n == 0 || !isfinite(v)) ? -INFINITY : __ddiv_rn(v, (double)n);
+        else v = isfinite(v) ? v : -INFINITY;       // all hypotheses share n_time: one division after the loop
+        if (v > best) { best = v; bh = h; }
+    }
+    if (!EDGE) best = (n_time == 0 || best == -INFINITY) ? -INFINITY : __ddiv_rn(best, (double)n_time);
+}
+
+#ifndef FT8B_DRIFT_MINB
+#define FT8B_DRIFT_MINB 1
+#endif
+__global__ void __launch_bounds__(kDriftStrip, FT8B_DRIFT_MINB)
+sync_scores_drift_tiled_kernel(const double *mag, int T, int F, int s, int b, int nb, int t0, int nt, int nf, int n_hyp,
+                               int max_shift, double *best_score, int32_t *best_hyp) {
+    extern __shared__ double tile[];                       // [21][wc] contrasts, then (EDGE) [21][wc] counts (bytes)
+    const int wc = kDriftStrip + 2 * max_shift;
+    unsigned char *cnt = reinterpret_cast<unsigned char *>(tile + kNumCells * wc);
+    const int f0 = blockIdx.x * kDriftStrip;
+    const int ti = blockIdx.y;
+    const int64_t slot = blockIdx.z;
+    const int at = t0 + ti;
+    int base = at / s;
+    if ((at % s) != 0 && at < 0) --base;
+    const double *m0 = mag + slot * (int64_t)T * F;
+    // every cell of this strip has all its bins inside the waterfall?
+    const bool edge = (f0 - max_shift < 0) || (f0 + kDriftStrip - 1 + max_shift + 7 * b >= F);
+    int n_time = 0;                                        // comparisons per score when no cell is lost in frequency
+    // Rows are dealt to the four warps; a lane forms kU contrasts per pass with all their loads issued up front (the
+    // tile is built from L2/L1 hits whose latency would otherwise be paid cell after cell).
+#ifndef FT8B_DRIFT_U
+#define FT8B_DRIFT_U 5
+#endif
+    constexpr int kU = FT8B_DRIFT_U;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int qi = 0; qi < kNumCells; ++qi) {
+        const int m = qi / kLenSync, k = qi - m * kLenSync;
+        const int q = m * kSyncOffset + k;
+        const int blk = base + q;
+        const int tone = c_costas[k];
+        const bool live = blk >= 0 && blk < nb;
+        const bool has_low = tone > 0;
+        const bool has_prev = k > 0 && blk > 0;
+        const bool has_next = k < kLenSync - 1 && blk + 1 < nb;
+        const int n_cell = live ? (int)has_low + 1 + (int)has_prev + (int)has_next : 0;
+        n_time += n_cell;
+        if ((qi & 3) != warp) continue;
+        double *row = tile + qi * wc;
+        const double *col = m0 + (int64_t)(at + q * s) * F;
+        const int64_t step = (int64_t)s * F;
+        const int x0 = f0 - max_shift + tone * b;            // bin of tile column 0 in this row
+        const int lo_b = has_low ? b : 0;
+        for (int j0 = lane; j0 < wc; j0 += 32 * kU) {
+            double p[kU], hi[kU], lo[kU], pv[kU], nx[kU];
+            bool ok[kU];
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                const int x = x0 + j0 + 32 * u;
+                ok[u] = live && j0 + 32 * u < wc && x - lo_b >= 0 && x + b < F;
+                p[u] = hi[u] = lo[u] = pv[u] = nx[u] = 0.0;
+                if (ok[u]) {
+                    p[u] = __ldg(col + x);
+                    hi[u] = __ldg(col + x + b);
+                    if (has_low) lo[u] = __ldg(col + x - b);
+                    if (has_prev) pv[u] = __ldg(col - step + x);
+                    if (has_next) nx[u] = __ldg(col + step + x);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                const int j = j0 + 32 * u;
+                if (j >= wc) break;
+                double c = 0.0;
+                if (ok[u]) {
+                    c = __dsub_rn(p[u], hi[u]);
+                    if (has_low) c = __dadd_rn(__dsub_rn(p[u], lo[u]), c);
+                    if (has_prev) c = __dadd_rn(c, __dsub_rn(p[u], pv[u]));
+                    if (has_next) c = __dadd_rn(c, __dsub_rn(p[u], nx[u]));
+                }
+                row[j] = c;
+                if (edge) cnt[qi * wc + j] = ok[u] ? (unsigned char)n_cell : (unsigned char)0;
+            }
+        }
+    }
+    __syncthreads();
+    const int f = f0 + threadIdx.x;
+    if (f >= nf) return;
+    double best;
+    int bh;
+    const char *tile_thread = reinterpret_cast<const char *>(tile + threadIdx.x);
+    if (edge) drift_walk<true>(tile_thread, cnt + threadIdx.x, n_hyp, n_time, best, bh);
+    else drift_walk<false>(tile_thread, nullptr, n_hyp, n_time, best, bh);
+    const int64_t o = (slot * nt + ti) * (int64_t)nf + f;
+    best_score[o] = best;
+    best_hyp[o] = bh;
+}
+
+static int drift_prepare(const double *mag, const double *d, const double *best_score, const int32_t *best_hyp, int n_hyp,
+                         int T, int F, int s, int b) {
+    if (!mag || !d || !best_score || !best_hyp) FT8B_ARG_FAIL("ft8b_sync_scores_drift: null pointer");
     if (n_hyp < 1 || n_hyp > kMaxDriftHyp) FT8B_ARG_FAIL("ft8b_sync_scores_drift: 1 <= n_hyp <= %d", kMaxDriftHyp);
     if (T < 0 || F < 0 || s < 1 || b < 1) FT8B_ARG_FAIL("ft8b_sync_scores_drift: bad shape");
+    for (int h = 0; h < n_hyp; ++h)
+        if (!std::isfinite(d[h]) || std::fabs(d[h]) > 1e6) FT8B_ARG_FAIL("ft8b_sync_scores_drift: hypothesis %d is not a finite drift", h);
+    return 0;
+}
+
+int sync_scores_drift(const double *mag, int64_t n_slots, int T, int F, int s, int b, int n_hyp,
+                      const double *drift_bins_per_symbol, double *best_score, int32_t *best_hyp, int direct,
+                      cudaStream_t stream) {
+    if (int rc = drift_prepare(mag, drift_bins_per_symbol, best_score, best_hyp, n_hyp, T, F, s, b)) return rc;
     int t0, nt, nf;
     ft8b_search_ranges(T, F, s, b, &t0, &nt, &nf);
     if (n_slots <= 0 || nt <= 0 || nf <= 0) return 0;
     if (nt > 65535 || n_slots > 65535) FT8B_ARG_FAIL("ft8b_sync_scores_drift: too many time offsets / slots per call");
-    FT8B_CUDA_TRY(cudaMemcpyToSymbolAsync(c_drift, drift_bins_per_symbol, sizeof(double) * n_hyp, 0, cudaMemcpyHostToDevice, stream));
-    dim3 grid((nf + 127) / 128, nt, (unsigned)n_slots);
-    sync_scores_drift_kernel<<<grid, 128, 0, stream>>>(mag, T, F, s, b, T / s, t0, nt, nf, n_hyp, best_score, best_hyp);
-    FT8B_LAUNCH_CHECK("sync_scores_drift_kernel");
+    // shift(h, q) = round-half-even(d_h * q), the same expression the direct kernel and the LLR extraction evaluate
+    int shift[kMaxDriftHyp * kNumCells];
+    long max_shift = 0;
+    for (int h = 0; h < n_hyp; ++h)
+        for (int qi = 0; qi < kNumCells; ++qi) {
+            const int q = (qi / kLenSync) * kSyncOffset + qi % kLenSync;
+            const long sh = std::lrint(drift_bins_per_symbol[h] * (double)q);
+            shift[h * kNumCells + qi] = (int)sh;
+            if (std::labs(sh) > max_shift) max_shift = std::labs(sh);
+        }
+    if (direct || max_shift > kMaxDriftShift) {
+        FT8B_CUDA_TRY(cudaMemcpyToSymbolAsync(c_drift, drift_bins_per_symbol, sizeof(double) * n_hyp, 0, cudaMemcpyHostToDevice, stream));
+        dim3 grid((nf + 127) / 128, nt, (unsigned)n_slots);
+        sync_scores_drift_direct_kernel<<<grid, 128, 0, stream>>>(mag, T, F, s, b, T / s, t0, nt, nf, n_hyp, best_score, best_hyp);
+        FT8B_LAUNCH_CHECK("sync_scores_drift_direct_kernel");
+        return 0;
+    }
+    const int wc = kDriftStrip + 2 * (int)max_shift;
+    for (int i = 0; i < n_hyp * kNumCells; ++i) shift[i] = ((i % kNumCells) * wc + (int)max_shift + shift[i]) * (int)sizeof(double);
+    FT8B_CUDA_TRY(cudaMemcpyToSymbolAsync(c_cell_off, shift, sizeof(int) * n_hyp * kNumCells, 0, cudaMemcpyHostToDevice, stream));
+    const size_t smem = (size_t)kNumCells * wc * (sizeof(double) + 1);      // <= 48 384 B at kMaxDriftShift
+    dim3 grid((nf + kDriftStrip - 1) / kDriftStrip, nt, (unsigned)n_slots);
+    sync_scores_drift_tiled_kernel<<<grid, kDriftStrip, smem, stream>>>(mag, T, F, s, b, T / s, t0, nt, nf, n_hyp, (int)max_shift,
+                                                                        best_score, best_hyp);
+    FT8B_LAUNCH_CHECK("sync_scores_drift_tiled_kernel");
     return 0;
 }
 

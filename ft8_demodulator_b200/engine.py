@@ -130,19 +130,20 @@ def decode_candidates(mag, time_osr, freq_osr, cand_time, cand_freq, n_cand, max
     return out
 
 
-def sync_scores_drift(mag: torch.Tensor, time_osr: int, freq_osr: int, drift_bins_per_symbol):
+def sync_scores_drift(mag: torch.Tensor, time_osr: int, freq_osr: int, drift_bins_per_symbol, direct: bool = False):
     """Extension: best Costas score over linear-drift hypotheses.  Returns (best_score [B,nt,nf] f64,
-    best_hyp [B,nt,nf] i32, t0)."""
+    best_hyp [B,nt,nf] i32, t0).  `direct` selects the one-hypothesis-at-a-time kernel (cross-check of the tiled one)."""
     assert mag.is_cuda and mag.dtype == _F64 and mag.is_contiguous() and mag.dim() == 3
     B, T, F = mag.shape
     t0, nt, nf = _lib.search_ranges(T, F, time_osr, freq_osr)
     nt, nf = max(nt, 0), max(nf, 0)
     score = torch.empty((B, nt, nf), dtype=_F64, device=mag.device)
-    hyp = torch.zeros((B, nt, nf), dtype=torch.int32, device=mag.device)
+    hyp = torch.empty((B, nt, nf), dtype=torch.int32, device=mag.device)
     d = (C.c_double * len(drift_bins_per_symbol))(*[float(x) for x in drift_bins_per_symbol])
     if B and nt and nf:
-        _lib.check(_lib.lib().ft8b_sync_scores_drift(_p(mag), B, T, F, time_osr, freq_osr, len(drift_bins_per_symbol), d,
-                                                     _p(score), _p(hyp), _stream()), "ft8b_sync_scores_drift")
+        fn = _lib.lib().ft8b_sync_scores_drift_direct if direct else _lib.lib().ft8b_sync_scores_drift
+        _lib.check(fn(_p(mag), B, T, F, time_osr, freq_osr, len(drift_bins_per_symbol), d, _p(score), _p(hyp), _stream()),
+                   "ft8b_sync_scores_drift")
         torch.cuda.current_stream().synchronize()      # the hypothesis table lives in constant memory: one call at a time
     return score, hyp, t0
 

@@ -281,7 +281,7 @@ def decode_slots(waves, sample_rate, bins_per_tone: int = 2, steps_per_symbol: i
 
 def decode_slots_drift(waves, sample_rate, drift_hz_per_s, bins_per_tone: int = 2, steps_per_symbol: int = 2,
                        max_candidates: int = 20, min_score=10, max_iterations: int = 20, freq_min=None, freq_max=None,
-                       time_min=None, time_max=None, slots_per_pass: int = 64):
+                       time_min=None, time_max=None, slots_per_pass: int = 256):
     """EXTENSION (not in the reference; BASELINE north_star's drift-hypothesis sync for the satellite path):
     decode_slots with a Costas search over linear Doppler-drift hypotheses.
 

@@ -536,6 +536,48 @@ def test_drift_hypothesis_search_extension():
         assert any(abs(e - rates[i]) <= 0.75 for e in est), (rates[i], est)
 
 
+@pytest.mark.parametrize("F,T,s,b,hyps", [
+    (1920, 186, 2, 2, list(np.linspace(-0.17, 0.17, 29))),        # C4: +-3.33 Hz/s in bins per symbol
+    (961, 186, 2, 2, [0.0, 0.8, -0.8, 0.33, -0.05]),              # band-cropped, shifts up to 62 bins (widest tile)
+    (300, 120, 1, 1, [0.0, 0.4, -0.4, 0.123]),                    # osr 1x1, three strips of which two are edges
+    (700, 372, 4, 4, [0.0, -0.21, 0.21]),                         # osr 4x4
+    (1920, 186, 2, 2, [0.0, 1.5, -1.5]),                          # shifts beyond 64 bins: the direct kernel serves the call
+])
+def test_drift_sync_tiled_equals_direct(F, T, s, b, hyps):
+    """The tiled drift-hypothesis sync kernel (drift.cu: contrasts staged once per strip, hypotheses only pick where
+    to read) against the direct one-hypothesis-at-a-time kernel on random waterfalls: same best hypothesis, scores
+    within 1e-12 (the direct kernel sums in the reference's running order, ft8_decode.py:47-100)."""
+    g = torch.Generator(device="cuda").manual_seed(F + T)
+    mag = (torch.randn((3, T, F), generator=g, device="cuda", dtype=torch.float64) * 12.0 - 60.0).contiguous()
+    mag[1, 5, 17] = float("inf")            # non-finite cells make the scores that touch them -inf in both kernels
+    mag[2, T // 2, F // 2] = float("nan")
+    sa, ha, t0a = engine.sync_scores_drift(mag, s, b, hyps)
+    sb, hb, t0b = engine.sync_scores_drift(mag, s, b, hyps, direct=True)
+    assert t0a == t0b and sa.shape == sb.shape and sa.numel() > 0
+    fin = torch.isfinite(sb)
+    assert torch.equal(fin, torch.isfinite(sa))
+    assert torch.equal(sa[~fin], sb[~fin])
+    assert (sa[fin] - sb[fin]).abs().max().item() < 1e-12
+    same = ha == hb
+    if not bool(same.all()):
+        # a different winner is legitimate only between hypotheses whose scores agree to rounding
+        assert float((~same).float().mean()) < 1e-4
+        per_h = torch.stack([engine.sync_scores_drift(mag, s, b, [h], direct=True)[0] for h in hyps])
+        pick = lambda hh: per_h.gather(0, hh.long()[None])[0]
+        assert (pick(ha)[~same] - pick(hb)[~same]).abs().max().item() < 1e-12
+
+
+def test_drift_sync_single_hypothesis_is_the_plain_score_map():
+    """With the one hypothesis d = 0 both drift kernels return ft8b_sync_scores' map (ft8_decode.py:47-100)."""
+    g = torch.Generator(device="cuda").manual_seed(11)
+    mag = (torch.randn((2, 186, 1920), generator=g, device="cuda", dtype=torch.float64) * 12.0 - 60.0).contiguous()
+    ref, t0 = engine.sync_scores(mag, 2, 2)
+    for direct in (False, True):
+        sc, hyp, t0d = engine.sync_scores_drift(mag, 2, 2, [0.0], direct=direct)
+        assert t0d == t0 and not hyp.any()
+        assert (sc - ref).abs().max().item() < 1e-12
+
+
 def test_bp_division_matches_ieee():
     """The BP kernel's branch-free division (decode.cu div_rn_core) against IEEE division over the operand domain of
     fast_tanh / fast_atanh (ldpc_decoder.py:11-31): denominators in [60, 2.1e4], numerators of any magnitude."""

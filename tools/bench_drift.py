@@ -1,0 +1,91 @@
+#!/usr/bin/env python
+"""Config C4 of BASELINE.json (extension: drift-hypothesis Costas search, no counterpart in the reference):
+slots/s and (candidate x hypothesis) scores/s of decode_slots_drift on drifting bursts (+-50 Hz per slot).
+
+    python tools/bench_drift.py [n_slots] [n_hypotheses] [steps]       (default 512 slots, 28 hypotheses, 3 steps)
+One JSON line: end-to-end device time of the public call (audio resident in HBM), the share of the drift sync
+kernel (CUDA events around ft8b_sync_scores_drift on the same spectrograms) and the decode check (transmitted
+payload recovered).
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+from ft8_demodulator_b200 import engine, synth  # noqa: E402
+from ft8_demodulator_b200.ft8_demodulator import ft8_decode as fd  # noqa: E402
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 512
+n_hyp = int(sys.argv[2]) if len(sys.argv) > 2 else 28
+steps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+dev = engine.require_cuda()
+rng = np.random.default_rng(4)
+base = 8
+rates = rng.uniform(-3.33, 3.33, base)
+payloads = [bytes(rng.integers(0, 256, 9, dtype=np.uint8).tolist() + [0x50]) for _ in range(base)]
+slots = np.stack([synth.drifting_slot(payloads[i], seed=700 + i, drift_hz_s=float(rates[i]), f0=600.0 + 250 * i)
+                  for i in range(base)]).astype(np.float32)
+waves = torch.from_numpy(slots).to(dev).repeat((n + base - 1) // base, 1)[:n].contiguous()
+hyps = np.linspace(-3.33, 3.33, n_hyp)
+kw = dict(bins_per_tone=2, steps_per_symbol=2, max_candidates=20, min_score=1, max_iterations=20)
+
+
+def ev():
+    return torch.cuda.Event(enable_timing=True)
+
+
+res, drift = fd.decode_slots_drift(waves, 12000, hyps, **kw)          # warm-up (tables, allocator)
+torch.cuda.synchronize()
+e0, e1 = ev(), ev()
+e0.record()
+for _ in range(steps):
+    res, drift = fd.decode_slots_drift(waves, 12000, hyps, **kw)
+e1.record()
+torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / steps
+# the sync kernels alone, on the spectrograms of the first slots: tiled (product) and direct (cross-check) kernel
+m = min(n, 256)
+g = fd.decode_geometry(waves.shape[1], 12000, 2, 2, None, None, None, None)
+mag = engine.stft_db(waves[:m], g["nperseg"], g["hop"], g["nfft"], g["bin_lo"], g["bin_hi"], g["frame_lo"], g["frame_hi"])
+d_bins = [0.0] + [float(r) * 0.16 / 3.125 for r in hyps if float(r) != 0.0]
+
+
+def time_sync(direct):
+    engine.sync_scores_drift(mag, 2, 2, d_bins, direct=direct)
+    torch.cuda.synchronize()
+    s0, s1 = ev(), ev()
+    s0.record()
+    for _ in range(steps):
+        out = engine.sync_scores_drift(mag, 2, 2, d_bins, direct=direct)
+    s1.record()
+    torch.cuda.synchronize()
+    return s0.elapsed_time(s1) / steps / m, out          # ms per slot
+
+
+sync_ms, (score, hyp, t0) = time_sync(False)
+direct_ms, (score_d, hyp_d, _) = time_sync(True)
+plain0, plain1 = ev(), ev()
+engine.sync_scores(mag, 2, 2)
+plain0.record()
+for _ in range(steps):
+    engine.sync_scores(mag, 2, 2)
+plain1.record()
+torch.cuda.synchronize()
+plain_ms = plain0.elapsed_time(plain1) / steps / m
+hit = sum(1 for i in range(n) if payloads[i % base] in res.payload_sets()[i])
+n_scores = score.shape[1] * score.shape[2] * len(d_bins)
+fin = torch.isfinite(score_d)
+print(json.dumps({"metric": "drift-hypothesis decode (C4 extension)", "n_slots": n, "hypotheses": len(d_bins),
+                  "ms_per_step": ms, "value": n / (ms * 1e-3), "unit": "slots/s",
+                  "sync_drift_us_per_slot": sync_ms * 1e3, "sync_drift_direct_us_per_slot": direct_ms * 1e3,
+                  "sync_plain_us_per_slot": plain_ms * 1e3, "sync_drift_share": sync_ms * n / ms,
+                  "scores_per_s": n_scores / (sync_ms * 1e-3), "scores_per_s_direct": n_scores / (direct_ms * 1e-3),
+                  "algorithmic_gbs_sync": (score.shape[1] * score.shape[2] * 12 + mag.shape[1] * mag.shape[2] * 8) / (sync_ms * 1e-3) / 1e9,
+                  "tiled_vs_direct": {"max_abs_score_diff": float((score[fin] - score_d[fin]).abs().max()),
+                                      "hyp_mismatch_fraction": float((hyp != hyp_d).float().mean())},
+                  "slots_with_tx_payload_decoded": hit}))
