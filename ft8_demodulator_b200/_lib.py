@@ -56,6 +56,9 @@ SIGNATURES = {
     "ft8b_decode_candidates_drift": (_i, [_vp, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp,
                                           _vp]),
     "ft8b_decode_workspace_bytes": (_i64, [C.POINTER(DecodeParams), _i64, _i64]),
+    "ft8b_decode_slots_host": (_i, [_vp, _i, _i64, _i64, _i64, C.POINTER(DecodeParams), _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp,
+                                    _vp, _vp, _vp]),
+    "ft8b_last_host_call_ms": (_d, []),
     "ft8b_decode_slots": (_i, [_vp, _i, _i64, _i64, _i64, C.POINTER(DecodeParams), _vp, _i64, _vp, _vp, _vp, _vp, _vp,
                                _vp, _vp, _vp, _vp, _vp]),
 }

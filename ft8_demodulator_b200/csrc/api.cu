@@ -38,6 +38,7 @@ int ldpc_crc_masked(const double *, const int32_t *, int, int64_t, int, uint8_t 
 int ldpc_check(const uint8_t *, int64_t, int32_t *, cudaStream_t);
 int selfcheck_divide(const double *, const double *, int64_t, int64_t *, cudaStream_t);
 int column_argmax(const double *, int64_t, int, int, int, int32_t *, cudaStream_t);
+int release_host_paths();
 int dechirp(const void *, int, int64_t, double, double, double2 *, cudaStream_t);
 
 // ---- optional per-stage timing (cudaEvent pairs on the launching stream), used by bench.py ----
@@ -115,7 +116,10 @@ extern "C" {
 
 int ft8b_version(void) { return FT8B_VERSION; }
 const char *ft8b_last_error(void) { return g_err; }
-int ft8b_release(void) { return release_plans(); }
+int ft8b_release(void) {
+    release_host_paths();
+    return release_plans();
+}
 int64_t ft8b_launch_count(void) { return g_launches.load(); }
 
 int ft8b_stage_timing(int enable) {

@@ -1,0 +1,275 @@
+// host.cu - ft8b_decode_slots_host: decode_ft8_message (ft8_decode.py:288-394) for a batch of slots that live in HOST
+// memory, results back in HOST memory.  This is the call a caller without any CUDA array library makes (the reference
+// is NumPy-only): plain pointers in, plain pointers out, the library owns streams and device memory.
+//
+// The batch is cut into pieces; the host-to-device copy of piece i+1 (copy stream) runs under the kernels of piece i
+// (compute stream) through two device audio buffers.  Pinned caller memory (cudaHostAlloc / cudaHostRegister, e.g. a
+// pinned torch tensor) is copied from directly; pageable memory (NumPy) is first gathered into two pinned staging
+// buffers by a few host threads, which overlaps as well because every device call here is asynchronous.
+// All device state is cached per device and reused by later calls (grow-only); ft8b_release() frees it.
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include "common.cuh"
+
+namespace ft8b {
+
+namespace {
+
+struct HostPath {
+    bool live = false;
+    cudaStream_t compute = nullptr, copy = nullptr;
+    cudaEvent_t ready[2] = {nullptr, nullptr};    // audio[k] filled (copy stream)
+    cudaEvent_t done[2] = {nullptr, nullptr};     // kernels finished with audio[k] (compute stream)
+    cudaEvent_t t_beg = nullptr, t_end = nullptr; // device-side span of one call (first copy .. results on the host)
+    void *audio[2] = {nullptr, nullptr};
+    size_t audio_bytes = 0;
+    void *stage[2] = {nullptr, nullptr};          // pinned staging for pageable callers
+    size_t stage_bytes = 0;
+    void *work = nullptr;
+    size_t work_bytes = 0;
+    char *res = nullptr;                          // device result arrays of one call
+    size_t res_bytes = 0;
+};
+
+constexpr int kMaxDevices = 64;
+double g_last_host_ms = 0.0;                      // ft8b_last_host_call_ms
+std::mutex g_host_mu;                             // host-buffer calls are serialised (they share the cached buffers)
+HostPath g_host[kMaxDevices];
+
+int grow(void **ptr, size_t *have, size_t need, bool pinned) {
+    if (*have >= need && *ptr) return 0;
+    if (*ptr) {
+        FT8B_CUDA_TRY(pinned ? cudaFreeHost(*ptr) : cudaFree(*ptr));
+        *ptr = nullptr;
+        *have = 0;
+    }
+    FT8B_CUDA_TRY(pinned ? cudaHostAlloc(ptr, need, cudaHostAllocDefault) : cudaMalloc(ptr, need));
+    *have = need;
+    return 0;
+}
+
+int init_path(HostPath &h) {
+    if (h.live) return 0;
+    FT8B_CUDA_TRY(cudaStreamCreateWithFlags(&h.compute, cudaStreamNonBlocking));
+    FT8B_CUDA_TRY(cudaStreamCreateWithFlags(&h.copy, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; ++k) {
+        FT8B_CUDA_TRY(cudaEventCreateWithFlags(&h.ready[k], cudaEventDisableTiming));
+        FT8B_CUDA_TRY(cudaEventCreateWithFlags(&h.done[k], cudaEventDisableTiming));
+    }
+    FT8B_CUDA_TRY(cudaEventCreate(&h.t_beg));
+    FT8B_CUDA_TRY(cudaEventCreate(&h.t_end));
+    h.live = true;
+    return 0;
+}
+
+void free_path(HostPath &h) {
+    if (!h.live) return;
+    for (int k = 0; k < 2; ++k) {
+        if (h.audio[k]) cudaFree(h.audio[k]);
+        if (h.stage[k]) cudaFreeHost(h.stage[k]);
+        if (h.ready[k]) cudaEventDestroy(h.ready[k]);
+        if (h.done[k]) cudaEventDestroy(h.done[k]);
+    }
+    if (h.t_beg) cudaEventDestroy(h.t_beg);
+    if (h.t_end) cudaEventDestroy(h.t_end);
+    if (h.work) cudaFree(h.work);
+    if (h.res) cudaFree(h.res);
+    if (h.compute) cudaStreamDestroy(h.compute);
+    if (h.copy) cudaStreamDestroy(h.copy);
+    h = HostPath();
+}
+
+// rows x row_bytes from a strided pageable source into a dense pinned buffer, split over a few threads
+void gather_rows(char *dst, const char *src, int64_t rows, size_t row_bytes, size_t src_pitch) {
+    const size_t total = (size_t)rows * row_bytes;
+    unsigned n_thr = std::thread::hardware_concurrency();
+    n_thr = std::max(1u, std::min(n_thr ? n_thr / 2 : 1u, 8u));
+    if (total < (8u << 20) || rows < 2) n_thr = 1;
+    n_thr = (unsigned)std::min<int64_t>(n_thr, rows);
+    auto run = [=](int64_t r0, int64_t r1) {
+        if (src_pitch == row_bytes) {
+            std::memcpy(dst + (size_t)r0 * row_bytes, src + (size_t)r0 * src_pitch, (size_t)(r1 - r0) * row_bytes);
+        } else {
+            for (int64_t r = r0; r < r1; ++r) std::memcpy(dst + (size_t)r * row_bytes, src + (size_t)r * src_pitch, row_bytes);
+        }
+    };
+    if (n_thr == 1) {
+        run(0, rows);
+        return;
+    }
+    std::vector<std::thread> pool;
+    for (unsigned t = 1; t < n_thr; ++t) pool.emplace_back(run, rows * t / n_thr, rows * (t + 1) / n_thr);
+    run(0, rows / n_thr);
+    for (auto &th : pool) th.join();
+}
+
+size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+}  // namespace
+
+int release_host_paths() {
+    std::lock_guard<std::mutex> lk(g_host_mu);
+    int cur = 0;
+    const bool have_cur = cudaGetDevice(&cur) == cudaSuccess;
+    for (int d = 0; d < kMaxDevices; ++d) {
+        if (!g_host[d].live) continue;
+        cudaSetDevice(d);
+        free_path(g_host[d]);
+    }
+    if (have_cur) cudaSetDevice(cur);
+    cudaGetLastError();
+    return 0;
+}
+
+}  // namespace ft8b
+
+using namespace ft8b;
+
+extern "C" int ft8b_decode_slots_host(const void *wave, int wave_dtype, int64_t n_slots, int64_t n_samples, int64_t slot_stride,
+                                      const ft8b_decode_params *p, int device, int64_t piece_slots, int32_t *cand_time,
+                                      int32_t *cand_freq, double *cand_score, int32_t *n_cand, uint8_t *ok,
+                                      int32_t *ldpc_errors, int32_t *crc_extracted, int32_t *crc_calculated,
+                                      uint8_t *payload) {
+    if (!p || (!wave && n_slots > 0) || !cand_time || !cand_freq || !cand_score || !n_cand || !ok || !ldpc_errors ||
+        !crc_extracted || !crc_calculated || !payload)
+        FT8B_ARG_FAIL("ft8b_decode_slots_host: null pointer");
+    if (wave_dtype != FT8B_DTYPE_F32 && wave_dtype != FT8B_DTYPE_F64 && wave_dtype != FT8B_DTYPE_I16)
+        FT8B_ARG_FAIL("ft8b_decode_slots_host: bad dtype");
+    if (n_slots < 0 || n_samples < 0 || slot_stride < n_samples) FT8B_ARG_FAIL("ft8b_decode_slots_host: bad shape");
+    if (p->max_candidates < 0 || p->max_candidates > FT8B_MAX_CANDIDATES) {
+        set_error("ft8b_decode_slots_host: max_candidates=%d outside [0,%d]", p->max_candidates, FT8B_MAX_CANDIDATES);
+        return FT8B_ERR_UNSUPPORTED;
+    }
+    if (n_slots == 0) return 0;
+    int dev = 0, n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev < 1) {
+        cudaGetLastError();
+        set_error("ft8b_decode_slots_host: no CUDA device (there is no CPU fallback)");
+        return FT8B_ERR_NO_DEVICE;
+    }
+    FT8B_CUDA_TRY(cudaGetDevice(&dev));
+    struct DeviceScope {      // run on `device` (if given) and put the caller's device back afterwards
+        int prev, cur;
+        ~DeviceScope() { if (cur != prev) cudaSetDevice(prev); }
+    } scope{dev, dev};
+    if (device >= 0 && device != dev) {
+        if (device >= n_dev) FT8B_ARG_FAIL("ft8b_decode_slots_host: device %d of %d", device, n_dev);
+        FT8B_CUDA_TRY(cudaSetDevice(device));
+        scope.cur = dev = device;
+    }
+    if (dev < 0 || dev >= kMaxDevices) FT8B_ARG_FAIL("ft8b_decode_slots_host: device ordinal %d", dev);
+
+    const int64_t K = p->max_candidates;
+    const size_t elt = wave_dtype == FT8B_DTYPE_F32 ? 4 : (wave_dtype == FT8B_DTYPE_I16 ? 2 : 8);
+    const size_t row_bytes = (size_t)n_samples * elt, src_pitch = (size_t)slot_stride * elt;
+    const int64_t piece = std::min<int64_t>(n_slots, piece_slots > 0 ? piece_slots : 128);
+    const int64_t work_need = ft8b_decode_workspace_bytes(p, piece, n_samples);
+    if (work_need < 0) return (int)work_need;     // geometry error, message already set
+
+    // is the caller's buffer page-locked (then the DMA engine reads it directly)?
+    cudaPointerAttributes attr;
+    bool pinned = false;
+    if (cudaPointerGetAttributes(&attr, wave) == cudaSuccess) {
+        if (attr.type == cudaMemoryTypeDevice) FT8B_ARG_FAIL("ft8b_decode_slots_host: wave is a device pointer (use ft8b_decode_slots)");
+        pinned = attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged;
+    } else {
+        cudaGetLastError();      // an address CUDA knows nothing about: pageable
+    }
+
+    std::lock_guard<std::mutex> lk(g_host_mu);
+    HostPath &h = g_host[dev];
+    int rc = init_path(h);
+    if (rc) return rc;
+    const int n_buf = n_slots > piece ? 2 : 1;
+    const size_t piece_bytes = std::max<size_t>((size_t)piece * row_bytes, 16);
+    if (h.audio_bytes < piece_bytes) {
+        for (int k = 0; k < 2; ++k) {
+            size_t have = h.audio[k] ? h.audio_bytes : 0;
+            if ((rc = grow(&h.audio[k], &have, piece_bytes, false))) return rc;
+        }
+        h.audio_bytes = piece_bytes;
+    }
+    if (!pinned && h.stage_bytes < piece_bytes) {
+        for (int k = 0; k < 2; ++k) {
+            size_t have = h.stage[k] ? h.stage_bytes : 0;
+            if ((rc = grow(&h.stage[k], &have, piece_bytes, true))) return rc;
+        }
+        h.stage_bytes = piece_bytes;
+    }
+    if ((rc = grow(&h.work, &h.work_bytes, (size_t)work_need, false))) return rc;
+    // device result arrays [n_slots][K]
+    const size_t nK = (size_t)n_slots * (size_t)K;
+    size_t off[10];
+    off[0] = 0;                                        // cand_time
+    off[1] = off[0] + align256(4 * nK);                // cand_freq
+    off[2] = off[1] + align256(4 * nK);                // cand_score
+    off[3] = off[2] + align256(8 * nK);                // n_cand
+    off[4] = off[3] + align256(4 * (size_t)n_slots);   // ok
+    off[5] = off[4] + align256(nK);                    // ldpc_errors
+    off[6] = off[5] + align256(4 * nK);                // crc_extracted
+    off[7] = off[6] + align256(4 * nK);                // crc_calculated
+    off[8] = off[7] + align256(4 * nK);                // payload
+    off[9] = off[8] + align256(10 * nK);
+    {
+        void *r = h.res;
+        if ((rc = grow(&r, &h.res_bytes, std::max<size_t>(off[9], 256), false))) return rc;
+        h.res = static_cast<char *>(r);
+    }
+    FT8B_CUDA_TRY(cudaEventRecord(h.t_beg, h.compute));
+    FT8B_CUDA_TRY(cudaMemsetAsync(h.res, 0, off[9], h.compute));
+    FT8B_CUDA_TRY(cudaStreamWaitEvent(h.copy, h.t_beg, 0));      // no copy of this call starts before its time origin
+
+    bool staged[2] = {false, false};
+    int64_t i = 0;
+    for (int64_t lo = 0; lo < n_slots; lo += piece, ++i) {
+        const int64_t n = std::min(piece, n_slots - lo);
+        const int k = (int)(i % n_buf);
+        const char *src = static_cast<const char *>(wave) + (size_t)lo * src_pitch;
+        size_t pitch = src_pitch;
+        if (!pinned) {
+            // stage[k] is free once the copy that last read it has finished
+            if (staged[k]) FT8B_CUDA_TRY(cudaEventSynchronize(h.ready[k]));
+            gather_rows(static_cast<char *>(h.stage[k]), src, n, row_bytes, src_pitch);
+            src = static_cast<const char *>(h.stage[k]);
+            pitch = row_bytes;
+            staged[k] = true;
+        }
+        if (i >= n_buf) FT8B_CUDA_TRY(cudaStreamWaitEvent(h.copy, h.done[k], 0));     // audio[k] no longer read
+        if (row_bytes > 0)
+            FT8B_CUDA_TRY(cudaMemcpy2DAsync(h.audio[k], row_bytes, src, pitch, row_bytes, (size_t)n, cudaMemcpyHostToDevice, h.copy));
+        FT8B_CUDA_TRY(cudaEventRecord(h.ready[k], h.copy));
+        FT8B_CUDA_TRY(cudaStreamWaitEvent(h.compute, h.ready[k], 0));
+        rc = ft8b_decode_slots(h.audio[k], wave_dtype, n, n_samples, n_samples, p, h.work, (int64_t)h.work_bytes,
+                               reinterpret_cast<int32_t *>(h.res + off[0]) + lo * K, reinterpret_cast<int32_t *>(h.res + off[1]) + lo * K,
+                               reinterpret_cast<double *>(h.res + off[2]) + lo * K, reinterpret_cast<int32_t *>(h.res + off[3]) + lo,
+                               reinterpret_cast<uint8_t *>(h.res + off[4]) + lo * K, reinterpret_cast<int32_t *>(h.res + off[5]) + lo * K,
+                               reinterpret_cast<int32_t *>(h.res + off[6]) + lo * K, reinterpret_cast<int32_t *>(h.res + off[7]) + lo * K,
+                               reinterpret_cast<uint8_t *>(h.res + off[8]) + lo * K * 10, h.compute);
+        if (rc) {
+            cudaStreamSynchronize(h.copy);
+            cudaStreamSynchronize(h.compute);
+            return rc;
+        }
+        FT8B_CUDA_TRY(cudaEventRecord(h.done[k], h.compute));
+    }
+    void *dst[9] = {cand_time, cand_freq, cand_score, n_cand, ok, ldpc_errors, crc_extracted, crc_calculated, payload};
+    const size_t len[9] = {4 * nK, 4 * nK, 8 * nK, 4 * (size_t)n_slots, nK, 4 * nK, 4 * nK, 4 * nK, 10 * nK};
+    for (int a = 0; a < 9; ++a)
+        if (len[a]) FT8B_CUDA_TRY(cudaMemcpyAsync(dst[a], h.res + off[a], len[a], cudaMemcpyDeviceToHost, h.compute));
+    FT8B_CUDA_TRY(cudaEventRecord(h.t_end, h.compute));
+    FT8B_CUDA_TRY(cudaStreamSynchronize(h.compute));
+    FT8B_CUDA_TRY(cudaStreamSynchronize(h.copy));
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h.t_beg, h.t_end) == cudaSuccess) g_last_host_ms = ms;
+    else cudaGetLastError();
+    return 0;
+}
+
+extern "C" double ft8b_last_host_call_ms(void) {
+    std::lock_guard<std::mutex> lk(g_host_mu);
+    return g_last_host_ms;
+}

@@ -298,6 +298,23 @@ class SlotDecoder:
         return o
 
 
+def decode_host_native(waves: torch.Tensor, params: _lib.DecodeParams, piece_slots: int = 128, device=None) -> SlotDecodes:
+    """Host [B, N] tensor -> HOST results through ft8b_decode_slots_host: the library's own C++ host path (two streams,
+    double-buffered audio, pinned staging for pageable input).  No torch CUDA tensor is involved; torch only provides the
+    host arrays here.  This is what decode_slots uses for host input."""
+    dev = device or require_cuda()
+    assert not waves.is_cuda and waves.dim() == 2 and waves.stride(1) == 1
+    B, N = waves.shape
+    K = params.max_candidates
+    out = alloc_slot_decodes(B, K, torch.device("cpu"))
+    if B:
+        _lib.check(_lib.lib().ft8b_decode_slots_host(
+            _p(waves), wave_dtype_code(waves), B, N, waves.stride(0), C.byref(params), dev.index if dev.index is not None else -1,
+            int(piece_slots), _p(out.cand_time), _p(out.cand_freq), _p(out.cand_score), _p(out.n_cand), _p(out.ok),
+            _p(out.ldpc_errors), _p(out.crc_extracted), _p(out.crc_calculated), _p(out.payload)), "ft8b_decode_slots_host")
+    return out
+
+
 def decode_host_batch(waves: torch.Tensor, params: _lib.DecodeParams, piece_slots: int = 128, device=None) -> SlotDecodes:
     """Host [B, N] tensor -> device results, with the H2D copy of piece i+1 overlapping the kernels of
     piece i (two device staging buffers, one copy stream).  Pinned host memory copies asynchronously."""

@@ -272,8 +272,12 @@ def decode_slots(waves, sample_rate, bins_per_tone: int = 2, steps_per_symbol: i
         out = engine.alloc_slot_decodes(B, int(max_candidates), dev)
     elif waves.is_cuda:
         out = engine.SlotDecoder(B, N, params, device=dev).run(waves if waves.stride(1) == 1 else waves.contiguous())
-    else:
+    elif return_device:
         out = engine.decode_host_batch(waves.contiguous(), params, piece_slots=piece_slots, device=dev)
+    else:       # host in, host out: the library's own host path (ft8b_decode_slots_host), no torch CUDA tensors involved
+        out = engine.decode_host_native(waves if waves.stride(1) == 1 else waves.contiguous(), params,
+                                        piece_slots=piece_slots, device=dev)
+        return BatchDecodes(out, sample_rate, bins_per_tone)
     if return_device:
         return out
     return BatchDecodes(out.cpu(), sample_rate, bins_per_tone)

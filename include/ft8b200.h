@@ -199,6 +199,23 @@ int ft8b_decode_slots(const void *wave, int wave_dtype, int64_t n_slots, int64_t
                       int32_t *cand_freq, double *cand_score, int32_t *n_cand, uint8_t *ok, int32_t *ldpc_errors,
                       int32_t *crc_extracted, int32_t *crc_calculated, uint8_t *payload, void *stream);
 
+/*
+ * The same path from HOST memory to HOST memory - the call a NumPy-only caller such as the reference makes (no CUDA
+ * array library needed; this is what `e2e` in bench.py times).  wave and all nine result arrays are host pointers;
+ * the library owns two streams, two device audio buffers, the chunk workspace and the device result arrays on
+ * `device` (-1 = the calling thread's current device; cached between calls, grow-only, freed by ft8b_release).  The batch runs in pieces of `piece_slots`
+ * slots (0 = 128): the host-to-device copy of piece i+1 overlaps the kernels of piece i.  Page-locked caller memory is
+ * copied from directly; pageable memory is gathered into pinned staging buffers by a few host threads first.
+ * Synchronous: the result arrays are complete when the call returns.  Calls are serialised inside the library.
+ */
+int ft8b_decode_slots_host(const void *wave, int wave_dtype, int64_t n_slots, int64_t n_samples, int64_t slot_stride,
+                           const ft8b_decode_params *p, int device, int64_t piece_slots, int32_t *cand_time, int32_t *cand_freq,
+                           double *cand_score, int32_t *n_cand, uint8_t *ok, int32_t *ldpc_errors,
+                           int32_t *crc_extracted, int32_t *crc_calculated, uint8_t *payload);
+/* Device-side duration (CUDA events: first copy enqueued .. last result byte on the host) of the most recent
+ * ft8b_decode_slots_host call of this process, in ms. */
+double ft8b_last_host_call_ms(void);
+
 /* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
 int64_t ft8b_launch_count(void);
 /* Per-stage device timing of ft8b_decode_slots (cudaEvent pairs on the launching stream).

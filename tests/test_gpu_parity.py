@@ -701,3 +701,67 @@ def test_concurrent_streams_and_threads():
     for k in range(2):
         for f in serial[k].__dataclass_fields__:
             assert torch.equal(getattr(serial[k], f), getattr(out[k], f)), (k, f)
+
+
+def _same_decodes(a, b):
+    return all(torch.equal(getattr(a, f).cpu(), getattr(b, f).cpu()) for f in a.__dataclass_fields__)
+
+
+def test_host_abi_path_equals_device_path():
+    """ft8b_decode_slots_host (host pointers in and out, the library's own streams, double buffering and pinned
+    staging) against ft8b_decode_slots on device-resident audio: pinned and pageable input, float32 / float64 / 16-bit
+    PCM, strided rows, batches that are not a multiple of the piece, a single slot, and the too-short slot."""
+    kw = dict(bins_per_tone=2, steps_per_symbol=2, max_candidates=20, min_score=1, max_iterations=20)
+    x = np.stack([synth.c3_slot(i)[0] for i in range(11)]).astype(np.float32)
+    ref = fd.decode_slots(torch.from_numpy(x).cuda(), 12000, return_device=True, **kw)
+    pinned = torch.empty(x.shape, dtype=torch.float32, pin_memory=True)
+    pinned.copy_(torch.from_numpy(x))
+    wide = np.zeros((11, x.shape[1] + 37), dtype=np.float32)
+    wide[:, :x.shape[1]] = x
+    for waves, piece in [(x, 128), (x, 4), (x, 1), (pinned, 4), (pinned, 11), (x.astype(np.float64), 3),
+                         (torch.from_numpy(wide)[:, :x.shape[1]], 5)]:
+        got = fd.decode_slots(waves, 12000, piece_slots=piece, **kw)
+        assert not got.arrays.ok.is_cuda and _same_decodes(got.arrays, ref), piece
+    one = fd.decode_slots(x[3], 12000, **kw)
+    assert _same_decodes(one.arrays, engine.slice_slot_decodes(ref, 3, 4))
+    q = np.round(x / np.abs(x).max(axis=1, keepdims=True) * 32767.0).astype(np.int16)
+    ref16 = fd.decode_slots(torch.from_numpy(q).cuda(), 12000, return_device=True, pcm16=True, **kw)
+    assert _same_decodes(fd.decode_slots(q, 12000, pcm16=True, piece_slots=4, **kw).arrays, ref16)
+    # K = 2000 (C2-sized candidate lists) through the host path, and a band/time mask
+    kw2 = dict(kw, max_candidates=2000, min_score=3, freq_max=3100.0, time_min=0.5)
+    assert _same_decodes(fd.decode_slots(x[:3], 12000, piece_slots=2, **kw2).arrays,
+                         fd.decode_slots(torch.from_numpy(x[:3]).cuda(), 12000, return_device=True, **kw2))
+    short = fd.decode_slots(np.zeros((2, 100), dtype=np.float32), 12000, **kw)
+    assert short.to_lists() == [[], []]
+    # the device-side duration of the last host call is reported
+    assert engine._lib.lib().ft8b_last_host_call_ms() > 0.0
+
+
+def test_host_abi_path_without_torch_tensors():
+    """The host entry point called the way a NumPy-only program would: ctypes + ndarray pointers, no torch objects."""
+    import ctypes as C
+    from ft8_demodulator_b200 import _lib
+    x = np.stack([synth.c3_slot(i)[0] for i in range(3)]).astype(np.float32)
+    g = fd.decode_geometry(x.shape[1], 12000, 2, 2, None, None, None, None)
+    prm = engine.make_params(12000, 2, 2, 20, 1, 20, g["bin_lo"], g["bin_hi"], g["frame_lo"], g["frame_hi"])
+    B, K = 3, 20
+    ct, cf, nc = np.zeros((B, K), np.int32), np.zeros((B, K), np.int32), np.zeros(B, np.int32)
+    cs, ok = np.zeros((B, K), np.float64), np.zeros((B, K), np.uint8)
+    le, ce, cc = np.zeros((B, K), np.int32), np.zeros((B, K), np.int32), np.zeros((B, K), np.int32)
+    pl = np.zeros((B, K, 10), np.uint8)
+    p = lambda a: a.ctypes.data
+    rc = _lib.lib().ft8b_decode_slots_host(p(x), _lib.DTYPE_F32, B, x.shape[1], x.shape[1], C.byref(prm), -1, 0, p(ct), p(cf),
+                                           p(cs), p(nc), p(ok), p(le), p(ce), p(cc), p(pl))
+    assert rc == 0, _lib.lib().ft8b_last_error()
+    ref = fd.decode_slots(torch.from_numpy(x).cuda(), 12000, return_device=True, bins_per_tone=2, steps_per_symbol=2,
+                          max_candidates=20, min_score=1, max_iterations=20).cpu()
+    assert np.array_equal(ct, ref.cand_time.numpy()) and np.array_equal(cf, ref.cand_freq.numpy())
+    assert np.array_equal(cs, ref.cand_score.numpy()) and np.array_equal(nc, ref.n_cand.numpy())
+    assert np.array_equal(ok, ref.ok.numpy()) and np.array_equal(le, ref.ldpc_errors.numpy())
+    assert np.array_equal(ce, ref.crc_extracted.numpy()) and np.array_equal(cc, ref.crc_calculated.numpy())
+    assert np.array_equal(pl, ref.payload.numpy())
+    # a device pointer is refused, not dereferenced on the host
+    d = torch.from_numpy(x).cuda()
+    rc = _lib.lib().ft8b_decode_slots_host(d.data_ptr(), _lib.DTYPE_F32, B, x.shape[1], x.shape[1], C.byref(prm), -1, 0, p(ct),
+                                           p(cf), p(cs), p(nc), p(ok), p(le), p(ce), p(cc), p(pl))
+    assert rc == _lib.ERR_ARG
