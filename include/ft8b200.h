@@ -10,11 +10,13 @@
  * Conventions
  *   - return 0 = OK, negative = argument / capability error (FT8B_ERR_*), positive = cudaError_t;
  *     ft8b_last_error() returns a thread-local description of the last failure.
- *   - every data pointer is a DEVICE pointer owned by the caller (contiguous, 16-byte aligned);
- *     the library allocates nothing per call.  Per-(device, nfft) window/twiddle tables are
- *     created on first use (mutex-guarded, synchronous) and live until ft8b_release().
- *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); every call is
- *     asynchronous on it.
+ *   - entry points that take a `stream`: every data pointer is a DEVICE pointer owned by the
+ *     caller (contiguous, 16-byte aligned); the library allocates nothing per call.
+ *     Per-(device, nfft) window/twiddle tables are created on first use (mutex-guarded,
+ *     synchronous) and live until ft8b_release().  `stream` is a cudaStream_t passed as void*
+ *     (NULL = legacy default stream); every call is asynchronous on it.
+ *   - ft8b_decode_slots_host is the one entry point on HOST pointers (audio in, results out):
+ *     the library owns streams and device buffers there, and the call is synchronous.
  *   - arithmetic is IEEE float64 throughout ("f64"): the reference computes in float64 for
  *     float64 audio, and bit-exact candidate/bit/payload parity needs it.  float32 audio is
  *     widened on load (exact).
