@@ -174,7 +174,7 @@ __device__ __forceinline__ void drift_walk(const char *tile_thread, const unsign
 }
 
 #ifndef FT8B_DRIFT_MINB
-#define FT8B_DRIFT_MINB 1
+#define FT8B_DRIFT_MINB 6
 #endif
 __global__ void __launch_bounds__(kDriftStrip, FT8B_DRIFT_MINB)
 sync_scores_drift_tiled_kernel(const double *mag, int T, int F, int s, int b, int nb, int t0, int nt, int nf, int n_hyp,

@@ -75,6 +75,34 @@ def test_no_cpu_fallback():
     # and the raw ABI reports a CUDA/no-device error instead of computing anything
     rc = _lib.lib().ft8b_ldpc_check(1, 1, 1, None)
     assert rc != 0
+    # the host-memory entry point: valid host arrays, no device -> FT8B_ERR_NO_DEVICE and untouched outputs
+    from ft8_demodulator_b200 import engine
+    x = np.zeros((2, 180000), dtype=np.float32)
+    prm = engine.make_params(12000, 2, 2, 20, 1, 20, 0, 1920, 0, 186)
+    outs = [np.full((2, 20), 7, np.int32), np.full((2, 20), 7, np.int32), np.full((2, 20), 7.0), np.full(2, 7, np.int32),
+            np.full((2, 20), 7, np.uint8), np.full((2, 20), 7, np.int32), np.full((2, 20), 7, np.int32),
+            np.full((2, 20), 7, np.int32), np.full((2, 20, 10), 7, np.uint8)]
+    rc = _lib.lib().ft8b_decode_slots_host(x.ctypes.data, _lib.DTYPE_F32, 2, 180000, 180000, C.byref(prm), -1, 0,
+                                           *[a.ctypes.data for a in outs])
+    assert rc == _lib.ERR_NO_DEVICE and "no CPU fallback" in _lib.last_error()
+    assert all((a == 7).all() for a in outs)
+
+
+def test_host_entry_argument_checks():
+    """ft8b_decode_slots_host rejects malformed calls before touching any device (runs without a GPU)."""
+    from ft8_demodulator_b200 import engine
+    prm = engine.make_params(12000, 2, 2, 20, 1, 20, 0, 1920, 0, 186)
+    x = np.zeros((1, 180000), dtype=np.float32)
+    o = [np.zeros(64 * 10, np.float64) for _ in range(9)]
+    ptrs = [a.ctypes.data for a in o]
+    L = _lib.lib()
+    assert L.ft8b_decode_slots_host(x.ctypes.data, 9, 1, 180000, 180000, C.byref(prm), -1, 0, *ptrs) == _lib.ERR_ARG       # dtype
+    assert L.ft8b_decode_slots_host(x.ctypes.data, _lib.DTYPE_F32, 1, 180000, 100, C.byref(prm), -1, 0, *ptrs) == _lib.ERR_ARG  # stride < n
+    assert L.ft8b_decode_slots_host(None, _lib.DTYPE_F32, 1, 180000, 180000, C.byref(prm), -1, 0, *ptrs) == _lib.ERR_ARG
+    assert L.ft8b_decode_slots_host(x.ctypes.data, _lib.DTYPE_F32, 1, 180000, 180000, C.byref(prm), -1, 0, *(ptrs[:8] + [None])) == _lib.ERR_ARG
+    big = engine.make_params(12000, 2, 2, 5000, 1, 20, 0, 1920, 0, 186)
+    assert L.ft8b_decode_slots_host(x.ctypes.data, _lib.DTYPE_F32, 1, 180000, 180000, C.byref(big), -1, 0, *ptrs) == _lib.ERR_UNSUPPORTED
+    assert L.ft8b_decode_slots_host(x.ctypes.data, _lib.DTYPE_F32, 0, 180000, 180000, C.byref(prm), -1, 0, *ptrs) == 0       # empty batch
 
 
 def test_product_never_imports_oracle():
