@@ -12,6 +12,7 @@ LIB_PATH = os.environ.get("FT8B_LIB_PATH") or os.path.join(_HERE, "libft8b200.so
 
 ERR_ARG, ERR_UNSUPPORTED, ERR_NO_DEVICE = -1, -2, -3
 DTYPE_F32, DTYPE_F64, DTYPE_I16, DTYPE_C64, DTYPE_C128 = 0, 1, 2, 3, 4
+DRIFT_AUTO, DRIFT_WALK, DRIFT_BLOCKSUM, DRIFT_DIRECT = 0, 1, 2, 3
 MAX_CANDIDATES = 4096
 LDPC_N = 174
 
@@ -52,7 +53,7 @@ SIGNATURES = {
     "ft8b_column_argmax": (_i, [_vp, _i64, _i, _i, _i, _vp, _vp]),
     "ft8b_dechirp": (_i, [_vp, _i, _i64, _d, _d, _vp, _vp]),
     "ft8b_sync_scores_drift": (_i, [_vp, _i64, _i, _i, _i, _i, _i, C.POINTER(C.c_double), _vp, _vp, _vp]),
-    "ft8b_sync_scores_drift_direct": (_i, [_vp, _i64, _i, _i, _i, _i, _i, C.POINTER(C.c_double), _vp, _vp, _vp]),
+    "ft8b_sync_scores_drift_variant": (_i, [_vp, _i64, _i, _i, _i, _i, _i, C.POINTER(C.c_double), _vp, _vp, _i, _vp]),
     "ft8b_decode_candidates_drift": (_i, [_vp, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp,
                                           _vp]),
     "ft8b_decode_workspace_bytes": (_i64, [C.POINTER(DecodeParams), _i64, _i64]),

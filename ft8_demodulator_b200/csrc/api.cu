@@ -213,9 +213,11 @@ int ft8b_sync_scores_drift(const double *mag, int64_t n_slots, int T, int F, int
                              (cudaStream_t)stream);
 }
 
-int ft8b_sync_scores_drift_direct(const double *mag, int64_t n_slots, int T, int F, int s, int b, int n_hyp,
-                                  const double *drift_bins_per_symbol, double *best_score, int32_t *best_hyp, void *stream) {
-    return sync_scores_drift(mag, n_slots, T, F, s, b, n_hyp, drift_bins_per_symbol, best_score, best_hyp, 1,
+int ft8b_sync_scores_drift_variant(const double *mag, int64_t n_slots, int T, int F, int s, int b, int n_hyp,
+                                   const double *drift_bins_per_symbol, double *best_score, int32_t *best_hyp, int variant,
+                                   void *stream) {
+    if (variant < 0 || variant > 3) FT8B_ARG_FAIL("ft8b_sync_scores_drift_variant: variant %d", variant);
+    return sync_scores_drift(mag, n_slots, T, F, s, b, n_hyp, drift_bins_per_symbol, best_score, best_hyp, variant,
                              (cudaStream_t)stream);
 }
 

@@ -4,7 +4,10 @@
 //   dechirp       : multiply by exp(-2*pi*i*(c2*n^2 + c3*n^3)), n = sample index        (:352-355, :598-634)
 // The regression / template-correlation logic around them is scalar host work on a few hundred points and stays
 // in the Python mirror.
+#include <algorithm>
 #include <cmath>
+#include <cstring>
+#include <mutex>
 
 #include "common.cuh"
 
@@ -176,6 +179,69 @@ __device__ __forceinline__ void drift_walk(const char *tile_thread, const unsign
 #ifndef FT8B_DRIFT_MINB
 #define FT8B_DRIFT_MINB 6
 #endif
+#ifndef FT8B_DRIFT_U
+#define FT8B_DRIFT_U 5
+#endif
+
+// The symbols of one Costas cell (block m, position k) for a candidate starting at abs_time `at`.
+struct DriftCell {
+    int q, tone, n_cell;
+    bool live, has_low, has_prev, has_next;
+};
+__device__ __forceinline__ DriftCell drift_cell(int qi, int base, int nb) {
+    DriftCell c;
+    const int m = qi / kLenSync, k = qi - m * kLenSync;
+    c.q = m * kSyncOffset + k;
+    const int blk = base + c.q;
+    c.tone = c_costas[k];
+    c.live = blk >= 0 && blk < nb;
+    c.has_low = c.tone > 0;
+    c.has_prev = k > 0 && blk > 0;
+    c.has_next = k < kLenSync - 1 && blk + 1 < nb;
+    c.n_cell = c.live ? (int)c.has_low + 1 + (int)c.has_prev + (int)c.has_next : 0;
+    return c;
+}
+
+// One warp forms one row of cell contrasts, row[j] = C(x0 + j), j < wc; a lane takes kU cells per pass with all their
+// loads issued up front (the tile is built from L2/L1 hits whose latency would otherwise be paid cell after cell).
+// cnt (edge strips only): comparisons behind each contrast, 0 where the cell's bins leave the waterfall.
+__device__ __forceinline__ void drift_contrast_row(const DriftCell &c, const double *col, int64_t step, int x0, int b, int F,
+                                                   int wc, int lane, double *row, unsigned char *cnt) {
+    constexpr int kU = FT8B_DRIFT_U;
+    const int lo_b = c.has_low ? b : 0;
+    for (int j0 = lane; j0 < wc; j0 += 32 * kU) {
+        double p[kU], hi[kU], lo[kU], pv[kU], nx[kU];
+        bool ok[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const int x = x0 + j0 + 32 * u;
+            ok[u] = c.live && j0 + 32 * u < wc && x - lo_b >= 0 && x + b < F;
+            p[u] = hi[u] = lo[u] = pv[u] = nx[u] = 0.0;
+            if (ok[u]) {
+                p[u] = __ldg(col + x);
+                hi[u] = __ldg(col + x + b);
+                if (c.has_low) lo[u] = __ldg(col + x - b);
+                if (c.has_prev) pv[u] = __ldg(col - step + x);
+                if (c.has_next) nx[u] = __ldg(col + step + x);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const int j = j0 + 32 * u;
+            if (j >= wc) break;
+            double v = 0.0;
+            if (ok[u]) {
+                v = __dsub_rn(p[u], hi[u]);
+                if (c.has_low) v = __dadd_rn(__dsub_rn(p[u], lo[u]), v);
+                if (c.has_prev) v = __dadd_rn(v, __dsub_rn(p[u], pv[u]));
+                if (c.has_next) v = __dadd_rn(v, __dsub_rn(p[u], nx[u]));
+            }
+            row[j] = v;
+            if (cnt) cnt[j] = ok[u] ? (unsigned char)c.n_cell : (unsigned char)0;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kDriftStrip, FT8B_DRIFT_MINB)
 sync_scores_drift_tiled_kernel(const double *mag, int T, int F, int s, int b, int nb, int t0, int nt, int nf, int n_hyp,
                                int max_shift, double *best_score, int32_t *best_hyp) {
@@ -192,61 +258,13 @@ sync_scores_drift_tiled_kernel(const double *mag, int T, int F, int s, int b, in
     // every cell of this strip has all its bins inside the waterfall?
     const bool edge = (f0 - max_shift < 0) || (f0 + kDriftStrip - 1 + max_shift + 7 * b >= F);
     int n_time = 0;                                        // comparisons per score when no cell is lost in frequency
-    // Rows are dealt to the four warps; a lane forms kU contrasts per pass with all their loads issued up front (the
-    // tile is built from L2/L1 hits whose latency would otherwise be paid cell after cell).
-#ifndef FT8B_DRIFT_U
-#define FT8B_DRIFT_U 5
-#endif
-    constexpr int kU = FT8B_DRIFT_U;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int qi = 0; qi < kNumCells; ++qi) {
-        const int m = qi / kLenSync, k = qi - m * kLenSync;
-        const int q = m * kSyncOffset + k;
-        const int blk = base + q;
-        const int tone = c_costas[k];
-        const bool live = blk >= 0 && blk < nb;
-        const bool has_low = tone > 0;
-        const bool has_prev = k > 0 && blk > 0;
-        const bool has_next = k < kLenSync - 1 && blk + 1 < nb;
-        const int n_cell = live ? (int)has_low + 1 + (int)has_prev + (int)has_next : 0;
-        n_time += n_cell;
+    for (int qi = 0; qi < kNumCells; ++qi) {               // rows are dealt to the four warps
+        const DriftCell c = drift_cell(qi, base, nb);
+        n_time += c.n_cell;
         if ((qi & 3) != warp) continue;
-        double *row = tile + qi * wc;
-        const double *col = m0 + (int64_t)(at + q * s) * F;
-        const int64_t step = (int64_t)s * F;
-        const int x0 = f0 - max_shift + tone * b;            // bin of tile column 0 in this row
-        const int lo_b = has_low ? b : 0;
-        for (int j0 = lane; j0 < wc; j0 += 32 * kU) {
-            double p[kU], hi[kU], lo[kU], pv[kU], nx[kU];
-            bool ok[kU];
-#pragma unroll
-            for (int u = 0; u < kU; ++u) {
-                const int x = x0 + j0 + 32 * u;
-                ok[u] = live && j0 + 32 * u < wc && x - lo_b >= 0 && x + b < F;
-                p[u] = hi[u] = lo[u] = pv[u] = nx[u] = 0.0;
-                if (ok[u]) {
-                    p[u] = __ldg(col + x);
-                    hi[u] = __ldg(col + x + b);
-                    if (has_low) lo[u] = __ldg(col + x - b);
-                    if (has_prev) pv[u] = __ldg(col - step + x);
-                    if (has_next) nx[u] = __ldg(col + step + x);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < kU; ++u) {
-                const int j = j0 + 32 * u;
-                if (j >= wc) break;
-                double c = 0.0;
-                if (ok[u]) {
-                    c = __dsub_rn(p[u], hi[u]);
-                    if (has_low) c = __dadd_rn(__dsub_rn(p[u], lo[u]), c);
-                    if (has_prev) c = __dadd_rn(c, __dsub_rn(p[u], pv[u]));
-                    if (has_next) c = __dadd_rn(c, __dsub_rn(p[u], nx[u]));
-                }
-                row[j] = c;
-                if (edge) cnt[qi * wc + j] = ok[u] ? (unsigned char)n_cell : (unsigned char)0;
-            }
-        }
+        drift_contrast_row(c, m0 + (int64_t)(at + c.q * s) * F, (int64_t)s * F, f0 - max_shift + c.tone * b, b, F, wc, lane,
+                           tile + qi * wc, edge ? cnt + qi * wc : nullptr);
     }
     __syncthreads();
     const int f = f0 + threadIdx.x;
@@ -256,6 +274,92 @@ sync_scores_drift_tiled_kernel(const double *mag, int T, int F, int s, int b, in
     const char *tile_thread = reinterpret_cast<const char *>(tile + threadIdx.x);
     if (edge) drift_walk<true>(tile_thread, cnt + threadIdx.x, n_hyp, n_time, best, bh);
     else drift_walk<false>(tile_thread, nullptr, n_hyp, n_time, best, bh);
+    const int64_t o = (slot * nt + ti) * (int64_t)nf + f;
+    best_score[o] = best;
+    best_hyp[o] = bh;
+}
+
+// Block-sum formulation (the one the library launches when it fits).  Within one Costas block the shift of a
+// hypothesis is base + delta_k with base = round(d * 36m) and a 7-entry pattern delta_k = shift(36m + k) - base that only
+// a handful of hypotheses-independent shapes can take (for |6d| <= 1.5: no step, or one step of +-1 at one of six
+// positions).  So the sum of a block's seven contrasts is formed ONCE per (pattern, frequency),
+//   B_m[pattern][x] = sum_k C_{m,k}(x + delta_k),
+// and a hypothesis reads three block sums, B_0[..][f + base_0] + B_1[..][f + base_1] + B_2[..][f + base_2], instead of
+// 21 contrasts: with 29 hypotheses the shared-memory loads per score drop from 21 to 3 + (patterns * 7 * (128 + 2
+// max|base|) / 128) / 29 ~ 12, with 128 hypotheses to ~5.  The contrast tile only ever holds one block (7 rows).
+// Same summation order as drift_walk: contrasts of a block in k order, then (B_0 + B_1) + B_2 - bit-identical scores.
+constexpr int kMaxDriftPatterns = 96;
+__device__ __constant__ int c_pat_off[kMaxDriftPatterns * kLenSync];     // element offset in the block's contrast tile: k*wc + G + delta_k
+__device__ __constant__ int c_pat_begin[kNumSync + 1];                   // pattern rows of block m: [begin[m], begin[m+1])
+__device__ __constant__ int c_bsum_off[kMaxDriftHyp * kNumSync];         // byte offset of (hypothesis, block) in the block-sum tile
+
+__global__ void __launch_bounds__(kDriftStrip, 4)
+sync_scores_drift_blocksum_kernel(const double *mag, int T, int F, int s, int b, int nb, int t0, int nt, int nf, int n_hyp,
+                                  int max_base, int guard, double *best_score, int32_t *best_hyp) {
+    extern __shared__ double tile[];
+    const int wb = kDriftStrip + 2 * max_base;             // block-sum columns: frequency offset f - f0 + max_base + base
+    const int margin = max_base + guard;
+    const int wc = kDriftStrip + 2 * margin;               // contrast columns: bin offset + margin
+    const int n_pat = c_pat_begin[kNumSync];
+    double *bsum = tile;                                   // [n_pat][wb]
+    double *con = bsum + n_pat * wb;                       // [7][wc], one Costas block at a time
+    unsigned char *bcnt = reinterpret_cast<unsigned char *>(con + kLenSync * wc);      // [n_pat][wb]   (edge strips)
+    unsigned char *ccnt = bcnt + n_pat * wb;                                           // [7][wc]
+    const int f0 = blockIdx.x * kDriftStrip;
+    const int ti = blockIdx.y;
+    const int64_t slot = blockIdx.z;
+    const int at = t0 + ti;
+    int base = at / s;
+    if ((at % s) != 0 && at < 0) --base;
+    const double *m0 = mag + slot * (int64_t)T * F;
+    const bool edge = (f0 - margin < 0) || (f0 + kDriftStrip - 1 + margin + 7 * b >= F);
+    int n_time = 0;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int m = 0; m < kNumSync; ++m) {
+        for (int k = 0; k < kLenSync; ++k) {
+            const DriftCell c = drift_cell(m * kLenSync + k, base, nb);
+            n_time += c.n_cell;
+            if ((k & 3) != warp) continue;
+            drift_contrast_row(c, m0 + (int64_t)(at + c.q * s) * F, (int64_t)s * F, f0 - margin + c.tone * b, b, F, wc, lane,
+                               con + k * wc, edge ? ccnt + k * wc : nullptr);
+        }
+        __syncthreads();
+        for (int r = c_pat_begin[m] + warp; r < c_pat_begin[m + 1]; r += 4) {      // pattern rows dealt to the warps
+            const int *off = c_pat_off + r * kLenSync;
+            for (int j = lane; j < wb; j += 32) {
+                double a = con[off[0] + j];
+#pragma unroll
+                for (int k = 1; k < kLenSync; ++k) a = __dadd_rn(a, con[off[k] + j]);
+                bsum[r * wb + j] = a;
+                if (edge) {
+                    int n = 0;
+#pragma unroll
+                    for (int k = 0; k < kLenSync; ++k) n += ccnt[off[k] + j];
+                    bcnt[r * wb + j] = (unsigned char)n;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    const int f = f0 + threadIdx.x;
+    if (f >= nf) return;
+    const char *mine = reinterpret_cast<const char *>(bsum + threadIdx.x);
+    const unsigned char *mine_cnt = bcnt + threadIdx.x;
+    double best = -INFINITY;
+    int bh = 0;
+    for (int h = 0; h < n_hyp; ++h) {
+        const int *off = c_bsum_off + h * kNumSync;
+        double v = __dadd_rn(__dadd_rn(*reinterpret_cast<const double *>(mine + off[0]), *reinterpret_cast<const double *>(mine + off[1])),
+                             *reinterpret_cast<const double *>(mine + off[2]));
+        if (edge) {
+            const int n = mine_cnt[off[0] >> 3] + mine_cnt[off[1] >> 3] + mine_cnt[off[2] >> 3];
+            v = (n == 0 || !isfinite(v)) ? -INFINITY : __ddiv_rn(v, (double)n);
+        } else {
+            v = isfinite(v) ? v : -INFINITY;
+        }
+        if (v > best) { best = v; bh = h; }
+    }
+    if (!edge) best = (n_time == 0 || best == -INFINITY) ? -INFINITY : __ddiv_rn(best, (double)n_time);
     const int64_t o = (slot * nt + ti) * (int64_t)nf + f;
     best_score[o] = best;
     best_hyp[o] = bh;
@@ -272,8 +376,10 @@ static int drift_prepare(const double *mag, const double *d, const double *best_
 }
 
 int sync_scores_drift(const double *mag, int64_t n_slots, int T, int F, int s, int b, int n_hyp,
-                      const double *drift_bins_per_symbol, double *best_score, int32_t *best_hyp, int direct,
+                      const double *drift_bins_per_symbol, double *best_score, int32_t *best_hyp, int mode,
                       cudaStream_t stream) {
+    // mode 0: the library's choice (block sums when they fit and pay, else the contrast walk, else direct);
+    // 1: contrast walk (or direct beyond its shift limit); 2: block sums or fail; 3: direct
     if (int rc = drift_prepare(mag, drift_bins_per_symbol, best_score, best_hyp, n_hyp, T, F, s, b)) return rc;
     int t0, nt, nf;
     ft8b_search_ranges(T, F, s, b, &t0, &nt, &nf);
@@ -289,12 +395,72 @@ int sync_scores_drift(const double *mag, int64_t n_slots, int T, int F, int s, i
             shift[h * kNumCells + qi] = (int)sh;
             if (std::labs(sh) > max_shift) max_shift = std::labs(sh);
         }
-    if (direct || max_shift > kMaxDriftShift) {
+    if (mode == 3 || max_shift > kMaxDriftShift) {
         FT8B_CUDA_TRY(cudaMemcpyToSymbolAsync(c_drift, drift_bins_per_symbol, sizeof(double) * n_hyp, 0, cudaMemcpyHostToDevice, stream));
         dim3 grid((nf + 127) / 128, nt, (unsigned)n_slots);
         sync_scores_drift_direct_kernel<<<grid, 128, 0, stream>>>(mag, T, F, s, b, T / s, t0, nt, nf, n_hyp, best_score, best_hyp);
         FT8B_LAUNCH_CHECK("sync_scores_drift_direct_kernel");
         return 0;
+    }
+    if (mode != 1) {
+        // block-sum plan: per block m the base shift and the pattern of the other six shifts relative to it
+        int pat[kMaxDriftPatterns][kLenSync], pat_block[kMaxDriftPatterns], n_pat = 0, begin[kNumSync + 1];
+        int row_of[kMaxDriftHyp * kNumSync], base_of[kMaxDriftHyp * kNumSync];
+        long max_base = 0, guard = 0;
+        bool fits = true;
+        for (int m = 0; m < kNumSync && fits; ++m) {
+            begin[m] = n_pat;
+            for (int h = 0; h < n_hyp && fits; ++h) {
+                const int *sh = shift + h * kNumCells + m * kLenSync;
+                int d[kLenSync];
+                for (int k = 0; k < kLenSync; ++k) {
+                    d[k] = sh[k] - sh[0];
+                    guard = std::max<long>(guard, std::labs((long)d[k]));
+                }
+                max_base = std::max<long>(max_base, std::labs((long)sh[0]));
+                int r = begin[m];
+                while (r < n_pat && std::memcmp(pat[r], d, sizeof(d)) != 0) ++r;
+                if (r == n_pat) {
+                    if (n_pat == kMaxDriftPatterns) { fits = false; break; }
+                    std::memcpy(pat[n_pat], d, sizeof(d));
+                    pat_block[n_pat++] = m;
+                }
+                row_of[h * kNumSync + m] = r;
+                base_of[h * kNumSync + m] = sh[0];
+            }
+        }
+        begin[kNumSync] = n_pat;
+        const int wb = kDriftStrip + 2 * (int)max_base, wcb = kDriftStrip + 2 * (int)(max_base + guard);
+        const size_t smem_b = ((size_t)n_pat * wb + (size_t)kLenSync * wcb) * (sizeof(double) + 1);
+        // worth it when three CTAs fit an SM and it reads less shared memory than the 21-contrast walk
+        constexpr size_t kBlocksumSmemMax = 75 * 1024;
+        const double loads_blocksum = 3.0 * n_hyp + 7.0 * n_pat * wb / kDriftStrip, loads_walk = 21.0 * n_hyp;
+        if (fits && max_base + guard <= kMaxDriftShift && smem_b <= kBlocksumSmemMax && (mode == 2 || loads_blocksum < 0.8 * loads_walk)) {
+            int pat_off[kMaxDriftPatterns * kLenSync], bsum_off[kMaxDriftHyp * kNumSync];
+            for (int r = 0; r < n_pat; ++r)
+                for (int k = 0; k < kLenSync; ++k) pat_off[r * kLenSync + k] = k * wcb + (int)guard + pat[r][k];
+            for (int i = 0; i < n_hyp * kNumSync; ++i) bsum_off[i] = (row_of[i] * wb + (int)max_base + base_of[i]) * (int)sizeof(double);
+            (void)pat_block;
+            FT8B_CUDA_TRY(cudaMemcpyToSymbolAsync(c_pat_off, pat_off, sizeof(int) * n_pat * kLenSync, 0, cudaMemcpyHostToDevice, stream));
+            FT8B_CUDA_TRY(cudaMemcpyToSymbolAsync(c_pat_begin, begin, sizeof(begin), 0, cudaMemcpyHostToDevice, stream));
+            FT8B_CUDA_TRY(cudaMemcpyToSymbolAsync(c_bsum_off, bsum_off, sizeof(int) * n_hyp * kNumSync, 0, cudaMemcpyHostToDevice, stream));
+            if (smem_b > 48 * 1024) {
+                static std::once_flag once[64];
+                int dev = 0;
+                FT8B_CUDA_TRY(cudaGetDevice(&dev));
+                cudaError_t e = cudaSuccess;
+                std::call_once(once[dev & 63], [&] {
+                    e = cudaFuncSetAttribute(sync_scores_drift_blocksum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBlocksumSmemMax);
+                });
+                if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(sync_scores_drift_blocksum_kernel)");
+            }
+            dim3 grid((nf + kDriftStrip - 1) / kDriftStrip, nt, (unsigned)n_slots);
+            sync_scores_drift_blocksum_kernel<<<grid, kDriftStrip, smem_b, stream>>>(mag, T, F, s, b, T / s, t0, nt, nf, n_hyp,
+                                                                                     (int)max_base, (int)guard, best_score, best_hyp);
+            FT8B_LAUNCH_CHECK("sync_scores_drift_blocksum_kernel");
+            return 0;
+        }
+        if (mode == 2) FT8B_ARG_FAIL("ft8b_sync_scores_drift: the block-sum kernel does not cover this hypothesis list");
     }
     const int wc = kDriftStrip + 2 * (int)max_shift;
     for (int i = 0; i < n_hyp * kNumCells; ++i) shift[i] = ((i % kNumCells) * wc + (int)max_shift + shift[i]) * (int)sizeof(double);

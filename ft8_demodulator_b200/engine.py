@@ -130,9 +130,10 @@ def decode_candidates(mag, time_osr, freq_osr, cand_time, cand_freq, n_cand, max
     return out
 
 
-def sync_scores_drift(mag: torch.Tensor, time_osr: int, freq_osr: int, drift_bins_per_symbol, direct: bool = False):
+def sync_scores_drift(mag: torch.Tensor, time_osr: int, freq_osr: int, drift_bins_per_symbol, variant: int = 0):
     """Extension: best Costas score over linear-drift hypotheses.  Returns (best_score [B,nt,nf] f64,
-    best_hyp [B,nt,nf] i32, t0).  `direct` selects the one-hypothesis-at-a-time kernel (cross-check of the tiled one)."""
+    best_hyp [B,nt,nf] i32, t0).  `variant` forces one of the three kernels (_lib.DRIFT_WALK / DRIFT_BLOCKSUM /
+    DRIFT_DIRECT; 0 = the library's choice) - for the cross-check tests and the A/B bench."""
     assert mag.is_cuda and mag.dtype == _F64 and mag.is_contiguous() and mag.dim() == 3
     B, T, F = mag.shape
     t0, nt, nf = _lib.search_ranges(T, F, time_osr, freq_osr)
@@ -141,8 +142,8 @@ def sync_scores_drift(mag: torch.Tensor, time_osr: int, freq_osr: int, drift_bin
     hyp = torch.empty((B, nt, nf), dtype=torch.int32, device=mag.device)
     d = (C.c_double * len(drift_bins_per_symbol))(*[float(x) for x in drift_bins_per_symbol])
     if B and nt and nf:
-        fn = _lib.lib().ft8b_sync_scores_drift_direct if direct else _lib.lib().ft8b_sync_scores_drift
-        _lib.check(fn(_p(mag), B, T, F, time_osr, freq_osr, len(drift_bins_per_symbol), d, _p(score), _p(hyp), _stream()),
+        _lib.check(_lib.lib().ft8b_sync_scores_drift_variant(_p(mag), B, T, F, time_osr, freq_osr, len(drift_bins_per_symbol),
+                                                             d, _p(score), _p(hyp), int(variant), _stream()),
                    "ft8b_sync_scores_drift")
         torch.cuda.current_stream().synchronize()      # the hypothesis table lives in constant memory: one call at a time
     return score, hyp, t0

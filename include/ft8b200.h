@@ -162,15 +162,26 @@ int ft8b_dechirp(const void *in, int in_dtype, int64_t n, double c2, double c3, 
  * ft8b_decode_candidates_drift extracts LLRs along each candidate's drift (cand_drift [n_slots][K], bins/symbol).
  * The hypothesis list is staged in constant memory in stream order: calls carrying DIFFERENT lists must not be in
  * flight on different streams of one device at the same time (every other entry point is free of such state).
- * ft8b_sync_scores_drift forms the 21 hypothesis-independent cell contrasts of a 128-frequency strip once in shared
- * memory and lets the hypotheses only choose where to read them (shifts up to 64 bins; larger ones take the direct
- * kernel); ft8b_sync_scores_drift_direct always evaluates the definition one hypothesis at a time with the reference's
- * running sum - same best_hyp, scores equal within 1e-12 - and exists as the cross-check of the tiled kernel.
+ * Three kernels compute the same map (same best_hyp; scores within 1e-12 of the reference's running sum):
+ *   FT8B_DRIFT_DIRECT    one thread per (time, frequency), every hypothesis evaluated from global memory with the
+ *                        reference's running sum; any shift; the cross-check of the other two
+ *   FT8B_DRIFT_WALK      the 21 hypothesis-independent cell contrasts of a 128-frequency strip are formed once in
+ *                        shared memory, a hypothesis only chooses where to read them (|shift| <= 64 bins)
+ *   FT8B_DRIFT_BLOCKSUM  additionally sums the seven contrasts of each Costas block once per distinct within-block
+ *                        shift pattern, so a hypothesis reads 3 block sums instead of 21 contrasts
+ * ft8b_sync_scores_drift picks BLOCKSUM when the hypothesis list has few enough patterns to fit and pay, else WALK,
+ * else DIRECT; ft8b_sync_scores_drift_variant forces one (FT8B_DRIFT_AUTO = the same choice; BLOCKSUM fails with
+ * FT8B_ERR_ARG when the list does not fit) and exists for the tests and the A/B bench.
  */
+#define FT8B_DRIFT_AUTO 0
+#define FT8B_DRIFT_WALK 1
+#define FT8B_DRIFT_BLOCKSUM 2
+#define FT8B_DRIFT_DIRECT 3
 int ft8b_sync_scores_drift(const double *mag, int64_t n_slots, int T, int F, int time_osr, int freq_osr, int n_hyp,
                            const double *drift_bins_per_symbol, double *best_score, int32_t *best_hyp, void *stream);
-int ft8b_sync_scores_drift_direct(const double *mag, int64_t n_slots, int T, int F, int time_osr, int freq_osr, int n_hyp,
-                                  const double *drift_bins_per_symbol, double *best_score, int32_t *best_hyp, void *stream);
+int ft8b_sync_scores_drift_variant(const double *mag, int64_t n_slots, int T, int F, int time_osr, int freq_osr, int n_hyp,
+                                   const double *drift_bins_per_symbol, double *best_score, int32_t *best_hyp, int variant,
+                                   void *stream);
 int ft8b_decode_candidates_drift(const double *mag, int64_t n_slots, int T, int F, int time_osr, int freq_osr,
                                  const int32_t *cand_time, const int32_t *cand_freq, const int32_t *n_cand,
                                  const double *cand_drift, int K, int max_iterations, uint8_t *ok, int32_t *ldpc_errors,

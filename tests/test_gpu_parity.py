@@ -542,29 +542,45 @@ def test_drift_hypothesis_search_extension():
     (300, 120, 1, 1, [0.0, 0.4, -0.4, 0.123]),                    # osr 1x1, three strips of which two are edges
     (700, 372, 4, 4, [0.0, -0.21, 0.21]),                         # osr 4x4
     (1920, 186, 2, 2, [0.0, 1.5, -1.5]),                          # shifts beyond 64 bins: the direct kernel serves the call
+    (1920, 186, 2, 2, [0.0] + list(np.linspace(-0.2, 0.2, 127))),  # the full 128-hypothesis list
+    (500, 186, 2, 2, [0.0, 0.45, -0.45, 0.3, -0.3, 0.7]),         # several steps inside a block (|6d| > 1.5)
 ])
 def test_drift_sync_tiled_equals_direct(F, T, s, b, hyps):
-    """The tiled drift-hypothesis sync kernel (drift.cu: contrasts staged once per strip, hypotheses only pick where
-    to read) against the direct one-hypothesis-at-a-time kernel on random waterfalls: same best hypothesis, scores
-    within 1e-12 (the direct kernel sums in the reference's running order, ft8_decode.py:47-100)."""
+    """The two tiled drift-hypothesis sync kernels (drift.cu: contrasts staged once per strip and walked per hypothesis;
+    block sums per within-block shift pattern) against the direct one-hypothesis-at-a-time kernel on random waterfalls:
+    same best hypothesis, scores within 1e-12 (the direct kernel sums in the reference's running order,
+    ft8_decode.py:47-100); walk and block sums agree bit for bit (same summation tree)."""
+    from ft8_demodulator_b200 import _lib
     g = torch.Generator(device="cuda").manual_seed(F + T)
     mag = (torch.randn((3, T, F), generator=g, device="cuda", dtype=torch.float64) * 12.0 - 60.0).contiguous()
-    mag[1, 5, 17] = float("inf")            # non-finite cells make the scores that touch them -inf in both kernels
+    mag[1, 5, 17] = float("inf")            # non-finite cells make the scores that touch them -inf in every kernel
     mag[2, T // 2, F // 2] = float("nan")
-    sa, ha, t0a = engine.sync_scores_drift(mag, s, b, hyps)
-    sb, hb, t0b = engine.sync_scores_drift(mag, s, b, hyps, direct=True)
-    assert t0a == t0b and sa.shape == sb.shape and sa.numel() > 0
+    sb, hb, t0b = engine.sync_scores_drift(mag, s, b, hyps, variant=_lib.DRIFT_DIRECT)
     fin = torch.isfinite(sb)
-    assert torch.equal(fin, torch.isfinite(sa))
-    assert torch.equal(sa[~fin], sb[~fin])
-    assert (sa[fin] - sb[fin]).abs().max().item() < 1e-12
-    same = ha == hb
-    if not bool(same.all()):
-        # a different winner is legitimate only between hypotheses whose scores agree to rounding
-        assert float((~same).float().mean()) < 1e-4
-        per_h = torch.stack([engine.sync_scores_drift(mag, s, b, [h], direct=True)[0] for h in hyps])
-        pick = lambda hh: per_h.gather(0, hh.long()[None])[0]
-        assert (pick(ha)[~same] - pick(hb)[~same]).abs().max().item() < 1e-12
+    per_h = None
+    got = {}
+    for variant in (_lib.DRIFT_AUTO, _lib.DRIFT_WALK, _lib.DRIFT_BLOCKSUM):
+        try:
+            sa, ha, t0a = engine.sync_scores_drift(mag, s, b, hyps, variant=variant)
+        except ValueError:
+            assert variant == _lib.DRIFT_BLOCKSUM and max(abs(h) for h in hyps) > 0.5       # list outside its cover
+            continue
+        got[variant] = (sa, ha)
+        assert t0a == t0b and sa.shape == sb.shape and sa.numel() > 0
+        assert torch.equal(fin, torch.isfinite(sa))
+        assert torch.equal(sa[~fin], sb[~fin])
+        assert (sa[fin] - sb[fin]).abs().max().item() < 1e-12
+        same = ha == hb
+        if not bool(same.all()):
+            # a different winner is legitimate only between hypotheses whose scores agree to rounding
+            assert float((~same).float().mean()) < 1e-4
+            if per_h is None:
+                per_h = torch.stack([engine.sync_scores_drift(mag, s, b, [h], variant=_lib.DRIFT_DIRECT)[0] for h in hyps])
+            pick = lambda hh: per_h.gather(0, hh.long()[None])[0]
+            assert (pick(ha)[~same] - pick(hb)[~same]).abs().max().item() < 1e-12
+    if _lib.DRIFT_BLOCKSUM in got:
+        assert torch.equal(got[_lib.DRIFT_WALK][0], got[_lib.DRIFT_BLOCKSUM][0])
+        assert torch.equal(got[_lib.DRIFT_WALK][1], got[_lib.DRIFT_BLOCKSUM][1])
 
 
 def test_drift_sync_single_hypothesis_is_the_plain_score_map():
@@ -572,8 +588,8 @@ def test_drift_sync_single_hypothesis_is_the_plain_score_map():
     g = torch.Generator(device="cuda").manual_seed(11)
     mag = (torch.randn((2, 186, 1920), generator=g, device="cuda", dtype=torch.float64) * 12.0 - 60.0).contiguous()
     ref, t0 = engine.sync_scores(mag, 2, 2)
-    for direct in (False, True):
-        sc, hyp, t0d = engine.sync_scores_drift(mag, 2, 2, [0.0], direct=direct)
+    for variant in (0, 1, 2, 3):
+        sc, hyp, t0d = engine.sync_scores_drift(mag, 2, 2, [0.0], variant=variant)
         assert t0d == t0 and not hyp.any()
         assert (sc - ref).abs().max().item() < 1e-12
 

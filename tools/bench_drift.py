@@ -55,20 +55,25 @@ mag = engine.stft_db(waves[:m], g["nperseg"], g["hop"], g["nfft"], g["bin_lo"], 
 d_bins = [0.0] + [float(r) * 0.16 / 3.125 for r in hyps if float(r) != 0.0]
 
 
-def time_sync(direct):
-    engine.sync_scores_drift(mag, 2, 2, d_bins, direct=direct)
+def time_sync(variant):
+    engine.sync_scores_drift(mag, 2, 2, d_bins, variant=variant)
     torch.cuda.synchronize()
     s0, s1 = ev(), ev()
     s0.record()
     for _ in range(steps):
-        out = engine.sync_scores_drift(mag, 2, 2, d_bins, direct=direct)
+        out = engine.sync_scores_drift(mag, 2, 2, d_bins, variant=variant)
     s1.record()
     torch.cuda.synchronize()
     return s0.elapsed_time(s1) / steps / m, out          # ms per slot
 
 
-sync_ms, (score, hyp, t0) = time_sync(False)
-direct_ms, (score_d, hyp_d, _) = time_sync(True)
+sync_ms, (score, hyp, t0) = time_sync(0)          # the library's choice
+walk_ms, _ = time_sync(1)
+try:
+    bsum_ms, _ = time_sync(2)
+except ValueError:
+    bsum_ms = None
+direct_ms, (score_d, hyp_d, _) = time_sync(3)
 plain0, plain1 = ev(), ev()
 engine.sync_scores(mag, 2, 2)
 plain0.record()
@@ -82,7 +87,9 @@ n_scores = score.shape[1] * score.shape[2] * len(d_bins)
 fin = torch.isfinite(score_d)
 print(json.dumps({"metric": "drift-hypothesis decode (C4 extension)", "n_slots": n, "hypotheses": len(d_bins),
                   "ms_per_step": ms, "value": n / (ms * 1e-3), "unit": "slots/s",
-                  "sync_drift_us_per_slot": sync_ms * 1e3, "sync_drift_direct_us_per_slot": direct_ms * 1e3,
+                  "sync_drift_us_per_slot": sync_ms * 1e3, "sync_drift_walk_us_per_slot": walk_ms * 1e3,
+                  "sync_drift_blocksum_us_per_slot": None if bsum_ms is None else bsum_ms * 1e3,
+                  "sync_drift_direct_us_per_slot": direct_ms * 1e3,
                   "sync_plain_us_per_slot": plain_ms * 1e3, "sync_drift_share": sync_ms * n / ms,
                   "scores_per_s": n_scores / (sync_ms * 1e-3), "scores_per_s_direct": n_scores / (direct_ms * 1e-3),
                   "algorithmic_gbs_sync": (score.shape[1] * score.shape[2] * 12 + mag.shape[1] * mag.shape[2] * 8) / (sync_ms * 1e-3) / 1e9,
