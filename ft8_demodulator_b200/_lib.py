@@ -60,6 +60,8 @@ SIGNATURES = {
     "ft8b_decode_slots_host": (_i, [_vp, _i, _i64, _i64, _i64, C.POINTER(DecodeParams), _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp,
                                     _vp, _vp, _vp]),
     "ft8b_last_host_call_ms": (_d, []),
+    "ft8b_set_host_staging": (_i, [_i, _i]),
+    "ft8b_selftest_host_staging": (_i, [_vp, _vp, _i64, _i64, _i64]),
     "ft8b_decode_slots": (_i, [_vp, _i, _i64, _i64, _i64, C.POINTER(DecodeParams), _vp, _i64, _vp, _vp, _vp, _vp, _vp,
                                _vp, _vp, _vp, _vp, _vp]),
 }

@@ -7,7 +7,12 @@
 // pinned torch tensor) is copied from directly; pageable memory (NumPy) is first gathered into two pinned staging
 // buffers by a few host threads, which overlaps as well because every device call here is asynchronous.
 // All device state is cached per device and reused by later calls (grow-only); ft8b_release() frees it.
+#include <emmintrin.h>
+
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <thread>
@@ -83,28 +88,147 @@ void free_path(HostPath &h) {
     h = HostPath();
 }
 
-// rows x row_bytes from a strided pageable source into a dense pinned buffer, split over a few threads
-void gather_rows(char *dst, const char *src, int64_t rows, size_t row_bytes, size_t src_pitch) {
-    const size_t total = (size_t)rows * row_bytes;
-    unsigned n_thr = std::thread::hardware_concurrency();
-    n_thr = std::max(1u, std::min(n_thr ? n_thr / 2 : 1u, 8u));
-    if (total < (8u << 20) || rows < 2) n_thr = 1;
-    n_thr = (unsigned)std::min<int64_t>(n_thr, rows);
-    auto run = [=](int64_t r0, int64_t r1) {
-        if (src_pitch == row_bytes) {
-            std::memcpy(dst + (size_t)r0 * row_bytes, src + (size_t)r0 * src_pitch, (size_t)(r1 - r0) * row_bytes);
-        } else {
-            for (int64_t r = r0; r < r1; ++r) std::memcpy(dst + (size_t)r * row_bytes, src + (size_t)r * src_pitch, row_bytes);
-        }
-    };
-    if (n_thr == 1) {
-        run(0, rows);
-        return;
+// Copy for the staging path: 16-byte non-temporal stores (the pinned destination is read next by the DMA engine, not by
+// a core, so it should not be pulled into the caches first: a cached store costs a read-for-ownership on top).
+void copy_stream(char *dst, const char *src, size_t n) {
+    const size_t head = std::min(n, (size_t)((16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15));
+    std::memcpy(dst, src, head);
+    dst += head; src += head; n -= head;
+    size_t i = 0;
+    for (; i + 64 <= n; i += 64) {
+        const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + i));
+        const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + i + 16));
+        const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + i + 32));
+        const __m128i d = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + i + 48));
+        _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i), a);
+        _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i + 16), b);
+        _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i + 32), c);
+        _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i + 48), d);
     }
-    std::vector<std::thread> pool;
-    for (unsigned t = 1; t < n_thr; ++t) pool.emplace_back(run, rows * t / n_thr, rows * (t + 1) / n_thr);
-    run(0, rows / n_thr);
-    for (auto &th : pool) th.join();
+    _mm_sfence();
+    std::memcpy(dst + i, src + i, n - i);
+}
+
+int env_int(const char *name, int dflt) {
+    const char *v = std::getenv(name);
+    return (v && *v) ? std::atoi(v) : dflt;
+}
+
+// Persistent host threads that gather pageable caller memory into the pinned staging buffers.  A job is a list of
+// blocks (256 KB pieces of a row) handed out through an atomic counter (cores of a shared box are not equally free); the calling thread
+// works too and returns when every block is done.  Created on first use, joined when the library is unloaded.
+class StagePool {
+public:
+    ~StagePool() {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto &t : threads_) t.join();
+    }
+    // rows x row_bytes from a strided source into a dense destination
+    void gather(char *dst, const char *src, int64_t rows, size_t row_bytes, size_t src_pitch) {
+        const size_t total = (size_t)rows * row_bytes;
+        if (rows <= 0 || row_bytes == 0) return;
+        const int want = workers_wanted(total, rows);
+        ensure_threads(want);
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            const int64_t segs = (int64_t)((row_bytes + kSegBytes - 1) / kSegBytes);      // blocks per row
+            job_ = Job{dst, src, rows * segs, segs, row_bytes, src_pitch, nt_};
+            next_.store(0, std::memory_order_relaxed);
+            left_.store(rows * segs, std::memory_order_relaxed);
+            active_ = want;
+            ++generation_;
+        }
+        if (want > 0) cv_.notify_all();
+        work();
+        // the last rows may still be in flight on other threads
+        std::unique_lock<std::mutex> lk(mu_);
+        done_cv_.wait(lk, [&] { return left_.load(std::memory_order_acquire) == 0 && busy_ == 0; });
+        active_ = 0;
+    }
+
+private:
+    static constexpr size_t kSegBytes = 256 << 10;
+    struct Job {
+        char *dst;
+        const char *src;
+        int64_t blocks, segs;
+        size_t row_bytes, src_pitch;
+        bool nt;
+    };
+public:
+    int configure(int threads, int nt) {       // threads <= 0: default; nt < 0: default
+        const int hc = (int)std::thread::hardware_concurrency();
+        // measured on the 16-thread B200 box (tools/stage_sweep.py): 1/2/4/6/8/10/12/16 threads stage 15.7/28.4/46.0/56.4/
+        // 61.5/60.8/58.8/57.6 k slots/s with streaming stores (cached stores: 12.2 ... 53.9 k at 8) - the memory system
+        // saturates at 8 copiers, so that is the default (and it leaves cores to the other ranks of a multi-GPU box)
+        const int dflt = std::max(1, std::min(hc > 2 ? hc - 2 : 1, 8));
+        n_cfg_ = std::max(1, std::min(threads > 0 ? threads : env_int("FT8B_STAGE_THREADS", dflt), 64));
+        nt_ = (nt >= 0 ? nt : env_int("FT8B_STAGE_NT", 1)) != 0;
+        return n_cfg_;
+    }
+
+private:
+    int workers_wanted(size_t total, int64_t rows) {
+        if (n_cfg_ < 0) configure(0, -1);
+        if (total < (8u << 20)) return 0;
+        return (int)std::min<int64_t>(n_cfg_ - 1, (int64_t)(total / kSegBytes));
+    }
+    void ensure_threads(int n) {
+        while ((int)threads_.size() < n) {
+            const int id = (int)threads_.size();
+            threads_.emplace_back([this, id] { loop(id); });
+        }
+    }
+    void work() {
+        const Job j = job_;
+        for (;;) {
+            const int64_t i = next_.fetch_add(1, std::memory_order_relaxed);
+            if (i >= j.blocks) break;
+            const int64_t r = i / j.segs;
+            const size_t o = (size_t)(i - r * j.segs) * kSegBytes, n = std::min(kSegBytes, j.row_bytes - o);
+            char *d = j.dst + (size_t)r * j.row_bytes + o;
+            const char *s = j.src + (size_t)r * j.src_pitch + o;
+            if (j.nt) copy_stream(d, s, n);
+            else std::memcpy(d, s, n);
+            left_.fetch_sub(1, std::memory_order_release);
+        }
+    }
+    void loop(int id) {
+        uint64_t seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return stop_ || (generation_ != seen && id < active_); });
+                if (stop_) return;
+                seen = generation_;
+                ++busy_;
+            }
+            work();
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                --busy_;
+            }
+            done_cv_.notify_one();
+        }
+    }
+    std::mutex mu_;
+    std::condition_variable cv_, done_cv_;
+    std::vector<std::thread> threads_;
+    Job job_{};
+    std::atomic<int64_t> next_{0}, left_{0};
+    uint64_t generation_ = 0;
+    int active_ = 0, busy_ = 0, n_cfg_ = -1;
+    bool nt_ = true, stop_ = false;
+};
+
+StagePool g_stage_pool;        // used under g_host_mu only
+
+void gather_rows(char *dst, const char *src, int64_t rows, size_t row_bytes, size_t src_pitch) {
+    g_stage_pool.gather(dst, src, rows, row_bytes, src_pitch);
 }
 
 size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -266,6 +390,18 @@ extern "C" int ft8b_decode_slots_host(const void *wave, int wave_dtype, int64_t 
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, h.t_beg, h.t_end) == cudaSuccess) g_last_host_ms = ms;
     else cudaGetLastError();
+    return 0;
+}
+
+extern "C" int ft8b_set_host_staging(int threads, int non_temporal) {
+    std::lock_guard<std::mutex> lk(g_host_mu);
+    return g_stage_pool.configure(threads, non_temporal != 0 ? 1 : 0);
+}
+
+extern "C" int ft8b_selftest_host_staging(void *dst, const void *src, int64_t rows, int64_t row_bytes, int64_t src_pitch) {
+    if (!dst || !src || rows < 0 || row_bytes < 0 || src_pitch < row_bytes) FT8B_ARG_FAIL("ft8b_selftest_host_staging: bad argument");
+    std::lock_guard<std::mutex> lk(g_host_mu);
+    gather_rows(static_cast<char *>(dst), static_cast<const char *>(src), rows, (size_t)row_bytes, (size_t)src_pitch);
     return 0;
 }
 

@@ -218,7 +218,8 @@ int ft8b_decode_slots(const void *wave, int wave_dtype, int64_t n_slots, int64_t
  * the library owns two streams, two device audio buffers, the chunk workspace and the device result arrays on
  * `device` (-1 = the calling thread's current device; cached between calls, grow-only, freed by ft8b_release).  The batch runs in pieces of `piece_slots`
  * slots (0 = 128): the host-to-device copy of piece i+1 overlaps the kernels of piece i.  Page-locked caller memory is
- * copied from directly; pageable memory is gathered into pinned staging buffers by a few host threads first.
+ * copied from directly; pageable memory is gathered into pinned staging buffers by persistent host threads first
+ * (streaming stores; ft8b_set_host_staging).
  * Synchronous: the result arrays are complete when the call returns.  Calls are serialised inside the library.
  */
 int ft8b_decode_slots_host(const void *wave, int wave_dtype, int64_t n_slots, int64_t n_samples, int64_t slot_stride,
@@ -228,6 +229,14 @@ int ft8b_decode_slots_host(const void *wave, int wave_dtype, int64_t n_slots, in
 /* Device-side duration (CUDA events: first copy enqueued .. last result byte on the host) of the most recent
  * ft8b_decode_slots_host call of this process, in ms. */
 double ft8b_last_host_call_ms(void);
+/* Host threads that gather pageable caller memory into the pinned staging buffers of ft8b_decode_slots_host
+ * (persistent, created on first use, the calling thread included in the count).  threads <= 0: the default
+ * (environment FT8B_STAGE_THREADS, else hardware threads - 2, at most 8); non_temporal != 0: write the staging buffers with
+ * streaming stores (default; environment FT8B_STAGE_NT).  Returns the thread count in effect. */
+int ft8b_set_host_staging(int threads, int non_temporal);
+/* Test hook (host only, no device needed): the staging gather itself - rows x row_bytes from a source of pitch
+ * src_pitch bytes into a dense destination, by the staging threads.  Returns 0. */
+int ft8b_selftest_host_staging(void *dst, const void *src, int64_t rows, int64_t row_bytes, int64_t src_pitch);
 
 /* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
 int64_t ft8b_launch_count(void);

@@ -112,3 +112,24 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "ft8_oracle" not in src and "reference_loader" not in src, f
+
+
+@pytest.mark.parametrize("threads,nt", [(1, 1), (3, 1), (4, 0), (0, 1)])
+def test_host_staging_gather(threads, nt):
+    """The pinned-staging gather of ft8b_decode_slots_host (persistent host threads, streaming stores) is host-only
+    code: strided and misaligned sources, rows larger and smaller than a 256 KB block, empty input - exact copies,
+    nothing written outside the destination."""
+    import numpy as np
+    L = _lib.lib()
+    assert L.ft8b_set_host_staging(threads, nt) >= 1
+    rng = np.random.default_rng(threads)
+    for rows, rb, pitch, off in ((40, 720000, 720000, 0), (33, 300001, 300013, 4), (200, 50003, 50011, 3),
+                                 (1, 9000001, 9000001, 1), (5, 17, 40, 0), (0, 10, 10, 0)):
+        src = rng.integers(0, 255, rows * pitch + 64, dtype=np.uint8)
+        dst = np.zeros(rows * rb + 64, dtype=np.uint8)
+        assert L.ft8b_selftest_host_staging(dst.ctypes.data + off, src.ctypes.data + off, rows, rb, pitch) == 0
+        want = src[off:off + rows * pitch].reshape(rows, pitch)[:, :rb].reshape(-1) if rows else src[:0]
+        assert np.array_equal(dst[off:off + rows * rb], want), (rows, rb, pitch)
+        assert not dst[:off].any() and not dst[off + rows * rb:].any()
+    assert L.ft8b_selftest_host_staging(None, None, 1, 1, 1) == _lib.ERR_ARG
+    L.ft8b_set_host_staging(0, 1)

@@ -29,5 +29,16 @@ llr, _ = synth.c5_llr(300, seed=2)
 print("bp", ld.bp_decode_batch(llr, 20)[1][:5], ld.ldpc_check(np.zeros(174)))
 xc = synth.c4_capture(seed=5, fs=12000, drift_hz_s=3.3, esn0_db=30.0)
 print("drift", fc.correct_frequency_drift(xc, 12000, 6.25, 0.16, {'steps_per_symbol': 8, 'debug_plots': False})[1] * 12000)
+from ft8_demodulator_b200 import _lib  # noqa: E402
+mag = engine.stft_db(w[:2], 1920, 960, 3840, 0, 1920, 0, 186)
+for variant, hyps in ((_lib.DRIFT_WALK, [0.0, 0.17, -0.17, 0.05]), (_lib.DRIFT_BLOCKSUM, [0.0, 0.17, -0.17, 0.05]),
+                      (_lib.DRIFT_DIRECT, [0.0, 1.5]), (_lib.DRIFT_AUTO, [0.0] + list(np.linspace(-0.2, 0.2, 127)))):
+    sc, hy, _ = engine.sync_scores_drift(mag, 2, 2, hyps, variant=variant)
+    print("drift sync variant", variant, float(sc[torch.isfinite(sc)].max()), int(hy.max()))
+ds = np.stack([synth.drifting_slot(bytes([7] * 9 + [0x50]), seed=3, drift_hz_s=3.3, f0=900.0)])
+found, dr = fd.decode_slots_drift(ds, 12000, np.arange(-4.0, 4.01, 0.5), max_candidates=20, min_score=1)
+print("drift decode", int(found.arrays.ok.sum()), float(dr.abs().max()))
+host = fd.decode_slots(np.ascontiguousarray(w[:3].cpu().numpy()), 12000, 2, 2, max_candidates=20, min_score=1)   # ft8b_decode_slots_host, pageable
+print("host abi", int(host.arrays.ok.sum()))
 torch.cuda.synchronize()
 print("sanitize smoke done")
