@@ -8,6 +8,7 @@
 // buffers by a few host threads, which overlaps as well because every device call here is asynchronous.
 // All device state is cached per device and reused by later calls (grow-only); ft8b_release() frees it.
 #include <emmintrin.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <atomic>
@@ -120,6 +121,10 @@ int env_int(const char *name, int dflt) {
 class StagePool {
 public:
     ~StagePool() {
+        if (!threads_.empty() && getpid() != pid_) {      // forked child: the threads do not exist here, nothing to join
+            new std::vector<std::thread>(std::move(threads_));
+            return;
+        }
         {
             std::lock_guard<std::mutex> lk(mu_);
             stop_ = true;
@@ -178,6 +183,7 @@ private:
         return (int)std::min<int64_t>(n_cfg_ - 1, (int64_t)(total / kSegBytes));
     }
     void ensure_threads(int n) {
+        if (threads_.empty()) pid_ = getpid();
         while ((int)threads_.size() < n) {
             const int id = (int)threads_.size();
             threads_.emplace_back([this, id] { loop(id); });
@@ -223,6 +229,7 @@ private:
     uint64_t generation_ = 0;
     int active_ = 0, busy_ = 0, n_cfg_ = -1;
     bool nt_ = true, stop_ = false;
+    pid_t pid_ = 0;
 };
 
 StagePool g_stage_pool;        // used under g_host_mu only
