@@ -37,7 +37,7 @@ for variant, hyps in ((_lib.DRIFT_WALK, [0.0, 0.17, -0.17, 0.05]), (_lib.DRIFT_B
     print("drift sync variant", variant, float(sc[torch.isfinite(sc)].max()), int(hy.max()))
 ds = np.stack([synth.drifting_slot(bytes([7] * 9 + [0x50]), seed=3, drift_hz_s=3.3, f0=900.0)])
 found, dr = fd.decode_slots_drift(ds, 12000, np.arange(-4.0, 4.01, 0.5), max_candidates=20, min_score=1)
-print("drift decode", int(found.arrays.ok.sum()), float(dr.abs().max()))
+print("drift decode", int(found.arrays.ok.sum()), float(np.abs(np.asarray(dr)).max()))
 host = fd.decode_slots(np.ascontiguousarray(w[:3].cpu().numpy()), 12000, 2, 2, max_candidates=20, min_score=1)   # ft8b_decode_slots_host, pageable
 print("host abi", int(host.arrays.ok.sum()))
 torch.cuda.synchronize()
