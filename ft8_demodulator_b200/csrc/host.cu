@@ -39,6 +39,8 @@ struct HostPath {
     size_t work_bytes = 0;
     char *res = nullptr;                          // device result arrays of one call
     size_t res_bytes = 0;
+    void *res_host = nullptr;                     // pinned mirror of res: ONE device-to-host copy per call
+    size_t res_host_bytes = 0;
 };
 
 constexpr int kMaxDevices = 64;
@@ -84,6 +86,7 @@ void free_path(HostPath &h) {
     if (h.t_end) cudaEventDestroy(h.t_end);
     if (h.work) cudaFree(h.work);
     if (h.res) cudaFree(h.res);
+    if (h.res_host) cudaFreeHost(h.res_host);
     if (h.compute) cudaStreamDestroy(h.compute);
     if (h.copy) cudaStreamDestroy(h.copy);
     h = HostPath();
@@ -173,13 +176,14 @@ public:
         const int dflt = std::max(1, std::min(hc > 2 ? hc - 2 : 1, 8));
         n_cfg_ = std::max(1, std::min(threads > 0 ? threads : env_int("FT8B_STAGE_THREADS", dflt), 64));
         nt_ = (nt >= 0 ? nt : env_int("FT8B_STAGE_NT", 1)) != 0;
+        min_bytes_ = (size_t)std::max(0, env_int("FT8B_STAGE_MIN_KB", 1024)) << 10;
         return n_cfg_;
     }
 
 private:
     int workers_wanted(size_t total, int64_t rows) {
         if (n_cfg_ < 0) configure(0, -1);
-        if (total < (8u << 20)) return 0;
+        if (total < min_bytes_) return 0;       // small inputs: waking threads costs more than it saves
         return (int)std::min<int64_t>(n_cfg_ - 1, (int64_t)(total / kSegBytes));
     }
     void ensure_threads(int n) {
@@ -229,6 +233,7 @@ private:
     uint64_t generation_ = 0;
     int active_ = 0, busy_ = 0, n_cfg_ = -1;
     bool nt_ = true, stop_ = false;
+    size_t min_bytes_ = 1u << 20;
     pid_t pid_ = 0;
 };
 
@@ -349,6 +354,7 @@ extern "C" int ft8b_decode_slots_host(const void *wave, int wave_dtype, int64_t 
         void *r = h.res;
         if ((rc = grow(&r, &h.res_bytes, std::max<size_t>(off[9], 256), false))) return rc;
         h.res = static_cast<char *>(r);
+        if ((rc = grow(&h.res_host, &h.res_host_bytes, std::max<size_t>(off[9], 256), true))) return rc;
     }
     FT8B_CUDA_TRY(cudaEventRecord(h.t_beg, h.compute));
     FT8B_CUDA_TRY(cudaMemsetAsync(h.res, 0, off[9], h.compute));
@@ -387,13 +393,16 @@ extern "C" int ft8b_decode_slots_host(const void *wave, int wave_dtype, int64_t 
         }
         FT8B_CUDA_TRY(cudaEventRecord(h.done[k], h.compute));
     }
-    void *dst[9] = {cand_time, cand_freq, cand_score, n_cand, ok, ldpc_errors, crc_extracted, crc_calculated, payload};
-    const size_t len[9] = {4 * nK, 4 * nK, 8 * nK, 4 * (size_t)n_slots, nK, 4 * nK, 4 * nK, 4 * nK, 10 * nK};
-    for (int a = 0; a < 9; ++a)
-        if (len[a]) FT8B_CUDA_TRY(cudaMemcpyAsync(dst[a], h.res + off[a], len[a], cudaMemcpyDeviceToHost, h.compute));
+    // results: one copy of the whole result block into the pinned mirror (nine copies into pageable caller arrays would
+    // each be staged and waited for by the driver), then plain memcpy into the caller's arrays
+    FT8B_CUDA_TRY(cudaMemcpyAsync(h.res_host, h.res, off[9], cudaMemcpyDeviceToHost, h.compute));
     FT8B_CUDA_TRY(cudaEventRecord(h.t_end, h.compute));
     FT8B_CUDA_TRY(cudaStreamSynchronize(h.compute));
     FT8B_CUDA_TRY(cudaStreamSynchronize(h.copy));
+    void *dst[9] = {cand_time, cand_freq, cand_score, n_cand, ok, ldpc_errors, crc_extracted, crc_calculated, payload};
+    const size_t len[9] = {4 * nK, 4 * nK, 8 * nK, 4 * (size_t)n_slots, nK, 4 * nK, 4 * nK, 4 * nK, 10 * nK};
+    for (int a = 0; a < 9; ++a)
+        if (len[a]) std::memcpy(dst[a], static_cast<const char *>(h.res_host) + off[a], len[a]);
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, h.t_beg, h.t_end) == cudaSuccess) g_last_host_ms = ms;
     else cudaGetLastError();

@@ -220,6 +220,7 @@ int ft8b_decode_slots(const void *wave, int wave_dtype, int64_t n_slots, int64_t
  * slots (0 = 128): the host-to-device copy of piece i+1 overlaps the kernels of piece i.  Page-locked caller memory is
  * copied from directly; pageable memory is gathered into pinned staging buffers by persistent host threads first
  * (streaming stores; ft8b_set_host_staging).
+ * The nine result arrays come back as ONE device-to-host copy into a pinned mirror and are then copied out on the host.
  * Synchronous: the result arrays are complete when the call returns.  Calls are serialised inside the library.
  */
 int ft8b_decode_slots_host(const void *wave, int wave_dtype, int64_t n_slots, int64_t n_samples, int64_t slot_stride,
@@ -232,7 +233,8 @@ double ft8b_last_host_call_ms(void);
 /* Host threads that gather pageable caller memory into the pinned staging buffers of ft8b_decode_slots_host
  * (persistent, created on first use, the calling thread included in the count).  threads <= 0: the default
  * (environment FT8B_STAGE_THREADS, else hardware threads - 2, at most 8); non_temporal != 0: write the staging buffers with
- * streaming stores (default; environment FT8B_STAGE_NT).  Returns the thread count in effect. */
+ * streaming stores (default; environment FT8B_STAGE_NT).  Inputs below FT8B_STAGE_MIN_KB (default 1024 KB) are
+ * gathered by the calling thread alone.  Returns the thread count in effect. */
 int ft8b_set_host_staging(int threads, int non_temporal);
 /* Test hook (host only, no device needed): the staging gather itself - rows x row_bytes from a source of pitch
  * src_pitch bytes into a dense destination, by the staging threads.  Returns 0. */

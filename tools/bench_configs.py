@@ -38,6 +38,13 @@ def latency(fn, n=20):
 c1 = synth.c1_slot()
 kw1 = dict(bins_per_tone=2, steps_per_symbol=2, max_candidates=20, min_score=1, max_iterations=20)
 c1_med, c1_min, r1 = latency(lambda: fd.decode_ft8_message(c1, 12000, **kw1))
+# where the C1 latency goes: device-side span of the host-ABI call (first copy enqueued .. results on the host, CUDA
+# events inside the library) against the wall clock of the Python call around it
+spans = []
+for _ in range(20):
+    fd.decode_ft8_message(c1, 12000, **kw1)
+    spans.append(engine._lib.lib().ft8b_last_host_call_ms())
+c1_span = float(np.median(spans))
 
 c2, payloads, *_ = synth.c2_slot()
 kw2 = dict(bins_per_tone=2, steps_per_symbol=2, max_candidates=2000, min_score=3, max_iterations=20, freq_max=3100.0)
@@ -59,7 +66,7 @@ torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 3
 n_cand = int(out.n_cand.sum())
 print(json.dumps({
-    "C1_single_slot": {"latency_ms_median": c1_med, "latency_ms_min": c1_min, "decodes": len(r1),
+    "C1_single_slot": {"latency_ms_median": c1_med, "latency_ms_min": c1_min, "decodes": len(r1), "device_span_ms_median": c1_span,
                        "payload": r1[0][0].payload.hex() if r1 else None, "reference_python_s_per_slot": 15.6},
     "C2_dense_band_K2000": {"latency_ms_median": c2_med, "latency_ms_min": c2_min, "decodes": len(r2),
                             "distinct_payloads": len(found), "transmitted_found": sum(p in found for p in payloads),
