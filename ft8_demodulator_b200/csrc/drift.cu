@@ -433,12 +433,12 @@ int sync_scores_drift(const double *mag, int64_t n_slots, int T, int F, int s, i
         const int wb = kDriftStrip + 2 * (int)max_base, wcb = kDriftStrip + 2 * (int)(max_base + guard);
         const size_t smem_b = ((size_t)n_pat * wb + (size_t)kLenSync * wcb) * (sizeof(double) + 1);
         // worth it when three CTAs fit an SM and it reads well under the shared memory of the 21-contrast walk: it runs
-        // at 4 instead of 6 CTAs per SM and builds the pattern rows first, so the break-even sits near half the walk's
-        // loads (tools/drift_variant_sweep.py, +-3.33 Hz/s: 17 / 29 / 57 / 128 hypotheses = load ratio 0.73 / 0.68 /
+        // at 4 instead of 6 CTAs per SM and builds the pattern rows first, so it only pays for longer hypothesis lists
+        // than the load count alone suggests (tools/drift_variant_sweep.py, +-3.33 Hz/s: 17 / 29 / 57 / 128 hypotheses = load ratio 0.73 / 0.68 /
         // 0.42 / 0.26 -> walk 23.4 / 31.6 / 53.9 / 111.9 us per slot, block sums 28.8 / 33.2 / 41.7 / 69.4)
         constexpr size_t kBlocksumSmemMax = 75 * 1024;
         const double loads_blocksum = 3.0 * n_hyp + 7.0 * n_pat * wb / kDriftStrip, loads_walk = 21.0 * n_hyp;
-        if (fits && max_base + guard <= kMaxDriftShift && smem_b <= kBlocksumSmemMax && (mode == 2 || loads_blocksum < 0.55 * loads_walk)) {
+        if (fits && max_base + guard <= kMaxDriftShift && smem_b <= kBlocksumSmemMax && (mode == 2 || (n_hyp >= 40 && loads_blocksum < 0.8 * loads_walk))) {
             int pat_off[kMaxDriftPatterns * kLenSync], bsum_off[kMaxDriftHyp * kNumSync];
             for (int r = 0; r < n_pat; ++r)
                 for (int k = 0; k < kLenSync; ++k) pat_off[r * kLenSync + k] = k * wcb + (int)guard + pat[r][k];
