@@ -253,16 +253,16 @@ def make_params(sample_rate, bins_per_tone, steps_per_symbol, max_candidates, mi
                              int(frame_hi), int(chunk_slots), 0)
 
 
-def alloc_slot_decodes(B: int, K: int, dev) -> SlotDecodes:
+def alloc_slot_decodes(B: int, K: int, dev, zero: bool = True) -> SlotDecodes:
+    """Result arrays of a batch; zero=False leaves them uninitialised (for callers that overwrite every element)."""
+    mk = torch.zeros if zero else torch.empty
+    i32, u8 = torch.int32, torch.uint8
     return SlotDecodes(
-        cand_time=torch.zeros((B, K), dtype=torch.int32, device=dev),
-        cand_freq=torch.zeros((B, K), dtype=torch.int32, device=dev),
-        cand_score=torch.zeros((B, K), dtype=_F64, device=dev), n_cand=torch.zeros((B,), dtype=torch.int32, device=dev),
-        ok=torch.zeros((B, K), dtype=torch.uint8, device=dev),
-        ldpc_errors=torch.zeros((B, K), dtype=torch.int32, device=dev),
-        crc_extracted=torch.zeros((B, K), dtype=torch.int32, device=dev),
-        crc_calculated=torch.zeros((B, K), dtype=torch.int32, device=dev),
-        payload=torch.zeros((B, K, 10), dtype=torch.uint8, device=dev))
+        cand_time=mk((B, K), dtype=i32, device=dev), cand_freq=mk((B, K), dtype=i32, device=dev),
+        cand_score=mk((B, K), dtype=_F64, device=dev), n_cand=mk((B,), dtype=i32, device=dev),
+        ok=mk((B, K), dtype=u8, device=dev), ldpc_errors=mk((B, K), dtype=i32, device=dev),
+        crc_extracted=mk((B, K), dtype=i32, device=dev), crc_calculated=mk((B, K), dtype=i32, device=dev),
+        payload=mk((B, K, 10), dtype=u8, device=dev))
 
 
 def slice_slot_decodes(o: SlotDecodes, lo: int, hi: int) -> SlotDecodes:
@@ -307,7 +307,7 @@ def decode_host_native(waves: torch.Tensor, params: _lib.DecodeParams, piece_slo
     assert not waves.is_cuda and waves.dim() == 2 and waves.stride(1) == 1
     B, N = waves.shape
     K = params.max_candidates
-    out = alloc_slot_decodes(B, K, torch.device("cpu"))
+    out = alloc_slot_decodes(B, K, torch.device("cpu"), zero=False)      # the library writes every element of all nine arrays
     if B:
         _lib.check(_lib.lib().ft8b_decode_slots_host(
             _p(waves), wave_dtype_code(waves), B, N, waves.stride(0), C.byref(params), dev.index if dev.index is not None else -1,

@@ -200,19 +200,19 @@ def decode_geometry(n_samples: int, sample_rate, bins_per_tone: int, steps_per_s
 
 
 def _results_from_arrays(out, slot: int, sample_rate, freq_osr: int) -> list:
-    """The reference's return list for one slot: successes in candidate order, 5-tuples (ft8_decode.py:383-391)."""
+    """The reference's return list for one slot: successes in candidate order, 5-tuples (ft8_decode.py:383-391).
+    `out`: SlotDecodes of host tensors, or the dict of NumPy views BatchDecodes keeps of them."""
+    a = out if isinstance(out, dict) else {f: getattr(out, f).numpy() for f in out.__dataclass_fields__}
+    n = int(a["n_cand"][slot])
     res = []
-    n = int(out.n_cand[slot])
-    for c in range(n):
-        if not out.ok[slot, c]:
-            continue
-        crc = int(out.crc_calculated[slot, c])
-        msg = FT8Message(payload=bytearray(out.payload[slot, c].numpy().tobytes()), hash=crc)
-        st = FT8DecodeStatus(ldpc_errors=int(out.ldpc_errors[slot, c]), crc_extracted=int(out.crc_extracted[slot, c]),
+    for c in np.flatnonzero(a["ok"][slot, :n]).tolist():       # scalar reads only for the successes
+        crc = int(a["crc_calculated"][slot, c])
+        msg = FT8Message(payload=bytearray(a["payload"][slot, c].tobytes()), hash=crc)
+        st = FT8DecodeStatus(ldpc_errors=int(a["ldpc_errors"][slot, c]), crc_extracted=int(a["crc_extracted"][slot, c]),
                              crc_calculated=crc)
-        abs_time, abs_freq = int(out.cand_time[slot, c]), int(out.cand_freq[slot, c])
+        abs_time, abs_freq = int(a["cand_time"][slot, c]), int(a["cand_freq"][slot, c])
         res.append((msg, st, abs_time / sample_rate, (abs_freq / freq_osr) * FT8_SYMBOL_FREQ_INTERVAL_HZ,
-                    float(out.cand_score[slot, c])))
+                    float(a["cand_score"][slot, c])))
     return res
 
 
@@ -221,12 +221,17 @@ class BatchDecodes:
 
     def __init__(self, arrays: engine.SlotDecodes, sample_rate, freq_osr: int):
         self.arrays, self.sample_rate, self.freq_osr = arrays, sample_rate, freq_osr
+        self._np = None             # NumPy views of the host tensors, made on first use
 
     def __len__(self):
         return self.arrays.n_cand.shape[0]
 
     def __getitem__(self, slot: int) -> list:
-        return _results_from_arrays(self.arrays, slot, self.sample_rate, self.freq_osr)
+        if self._np is None:
+            self._np = {f: getattr(self.arrays, f).numpy() for f in self.arrays.__dataclass_fields__}
+        if not -len(self) <= slot < len(self):
+            raise IndexError(slot)
+        return _results_from_arrays(self._np, slot, self.sample_rate, self.freq_osr)
 
     def to_lists(self) -> list:
         return [self[i] for i in range(len(self))]
