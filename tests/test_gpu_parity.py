@@ -781,3 +781,21 @@ def test_host_abi_path_without_torch_tensors():
     rc = _lib.lib().ft8b_decode_slots_host(d.data_ptr(), _lib.DTYPE_F32, B, x.shape[1], x.shape[1], C.byref(prm), -1, 0, p(ct),
                                            p(cf), p(cs), p(nc), p(ok), p(le), p(ce), p(cc), p(pl))
     assert rc == _lib.ERR_ARG
+
+
+def test_non_finite_audio_is_contained():
+    """Slots are independent: NaN / inf samples in one slot of a batch (a dropped SDR buffer) do not change the results of
+    its neighbours, the call returns, and the poisoned slots yield no successful decode."""
+    kw = dict(bins_per_tone=2, steps_per_symbol=2, max_candidates=20, min_score=1, max_iterations=20)
+    good = np.stack([synth.c3_slot(i)[0] for i in range(2)]).astype(np.float32)
+    bad_nan, bad_inf = good[0].copy(), good[1].copy()
+    bad_nan[50000:50010] = np.nan
+    bad_inf[1234] = np.inf
+    batch = np.stack([good[0], bad_nan, good[1], bad_inf, np.full_like(good[0], np.nan)])
+    alone = fd.decode_slots(good, 12000, **kw)
+    mixed = fd.decode_slots(batch, 12000, **kw)
+    for f in alone.arrays.__dataclass_fields__:
+        assert torch.equal(getattr(mixed.arrays, f)[[0, 2]], getattr(alone.arrays, f)), f
+    assert len(alone[0]) >= 1 and mixed[0] == alone[0] and mixed[2] == alone[1]
+    assert mixed[4] == []                               # all-NaN audio: nothing passes, nothing decodes
+    assert not mixed.arrays.ok[4].any()
