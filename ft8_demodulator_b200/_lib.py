@@ -14,6 +14,7 @@ ERR_ARG, ERR_UNSUPPORTED, ERR_NO_DEVICE = -1, -2, -3
 DTYPE_F32, DTYPE_F64, DTYPE_I16, DTYPE_C64, DTYPE_C128 = 0, 1, 2, 3, 4
 DRIFT_AUTO, DRIFT_WALK, DRIFT_BLOCKSUM, DRIFT_DIRECT = 0, 1, 2, 3
 MAX_CANDIDATES = 4096
+FLAG_STRICT_TOPK = 1
 LDPC_N = 174
 
 
@@ -23,7 +24,7 @@ class DecodeParams(C.Structure):
         ("sample_rate", C.c_double), ("bins_per_tone", C.c_int32), ("steps_per_symbol", C.c_int32),
         ("max_candidates", C.c_int32), ("max_iterations", C.c_int32), ("min_score", C.c_double),
         ("bin_lo", C.c_int32), ("bin_hi", C.c_int32), ("frame_lo", C.c_int64), ("frame_hi", C.c_int64),
-        ("chunk_slots", C.c_int32), ("reserved", C.c_int32),
+        ("chunk_slots", C.c_int32), ("flags", C.c_int32),
     ]
 
 
@@ -43,6 +44,7 @@ SIGNATURES = {
     "ft8b_stft_db": (_i, [_vp, _i, _i64, _i64, _i64, _i, _i, _i, _i, _i, _i64, _i64, _vp, _vp]),
     "ft8b_sync_scores": (_i, [_vp, _i64, _i, _i, _i, _i, _vp, _vp]),
     "ft8b_select_candidates": (_i, [_vp, _i64, _i, _i, _i, _i, _d, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ft8b_select_topk": (_i, [_vp, _i64, _i, _i, _i, _i, _d, _vp, _vp, _vp, _vp, _vp]),
     "ft8b_decode_candidates": (_i, [_vp, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                     _vp]),
     "ft8b_ldpc_crc": (_i, [_vp, _i64, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

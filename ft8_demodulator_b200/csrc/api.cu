@@ -190,6 +190,13 @@ int ft8b_select_candidates(const double *scores, int64_t n_slots, int nt, int nf
                              nullptr, 0, (cudaStream_t)stream);
 }
 
+int ft8b_select_topk(const double *scores, int64_t n_slots, int nt, int nf, int t0, int K, double min_score,
+                     int32_t *cand_time, int32_t *cand_freq, double *cand_score, int32_t *n_cand, void *stream) {
+    // n_tiles = -1 selects the strict top-K kernel
+    return select_candidates(scores, n_slots, nt, nf, t0, K, min_score, cand_time, cand_freq, cand_score, n_cand, nullptr,
+                             nullptr, -1, (cudaStream_t)stream);
+}
+
 int ft8b_decode_candidates(const double *mag, int64_t n_slots, int T, int F, int s, int b, const int32_t *cand_time,
                            const int32_t *cand_freq, const int32_t *n_cand, int K, int max_iterations, uint8_t *ok,
                            int32_t *ldpc_errors, int32_t *crc_extracted, int32_t *crc_calculated, uint8_t *payload,
@@ -331,8 +338,9 @@ int ft8b_decode_slots(const void *wave, int wave_dtype, int64_t n_slots, int64_t
         if (rc) return rc;
         {
             StageScope t(2, stream);
+            const bool strict = (p->flags & FT8B_FLAG_STRICT_TOPK) != 0;       // opt-in extension, see ft8b_select_topk
             rc = select_candidates(scores, nb, g.nt, g.nf, g.t0, K, p->min_score, cand_time + s0 * K, cand_freq + s0 * K,
-                                   cand_score + s0 * K, n_cand + s0, nullptr, tiles, cp.n_tiles, stream);
+                                   cand_score + s0 * K, n_cand + s0, nullptr, strict ? nullptr : tiles, strict ? -1 : cp.n_tiles, stream);
         }
         if (rc) return rc;
         {

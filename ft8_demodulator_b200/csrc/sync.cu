@@ -468,6 +468,146 @@ __global__ void __launch_bounds__(kSelThreads) select_candidates_kernel(const Se
 }
 
 // ------------------------------------------------------------------------------------------
+// Strict top-K selection - OPT-IN EXTENSION, not the reference's behaviour (the reference keeps the
+// first K passers in scan order plus one record replacement, ft8_decode.py:127-140; with one strong signal and
+// min_score = 1 that list is the signal plus K-1 noise cells from the first time row).  Here: the K best passers by
+// (score descending, scan position ascending), in that order.  One CTA per slot: radix select (8 bits per pass over an
+// order-preserving 64-bit key) finds the K-th best score, one more ordered pass gathers everything above it plus the
+// earliest ties, then the same bitonic sort as the reference-semantics kernel.
+__device__ __forceinline__ unsigned long long sel_key(double v) {          // larger double <=> larger key
+    const unsigned long long b = (unsigned long long)__double_as_longlong(__dadd_rn(v, 0.0));     // -0.0 -> +0.0: equal scores, equal keys
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+
+__global__ void __launch_bounds__(kSelThreads) select_topk_kernel(const SelArgs a) {
+    extern __shared__ unsigned char sel_smem[];
+    double *hs = reinterpret_cast<double *>(sel_smem);                   // [Kpad] scores
+    long long *hi = reinterpret_cast<long long *>(hs + a.Kpad);          // [Kpad] scan indices
+    __shared__ int hist[256];
+    __shared__ int warp_cnt[32];
+    __shared__ int s_bucket, s_need, s_base, s_tot, s_fill;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int64_t slot = blockIdx.x;
+    const double *sc = a.scores + slot * a.L;
+    const int K = a.K;
+    for (int i = tid; i < a.Kpad; i += kSelThreads) { hs[i] = -INFINITY; hi[i] = 0x7fffffffffffffffLL; }
+    if (tid == 0) { s_need = K; s_fill = 0; s_base = 0; }
+
+    // ---- radix select: after the pass at `shift`, `prefix` holds the top bits of the K-th best key ----
+    unsigned long long prefix = 0, mask = 0;
+    bool take_all = false;          // fewer than K passers: everything that passes is taken
+    for (int shift = 56; shift >= 0; shift -= 8) {
+        for (int i = tid; i < 256; i += kSelThreads) hist[i] = 0;
+        __syncthreads();
+        for (int64_t i = tid; i < a.L; i += kSelThreads) {
+            const double v = __ldg(sc + i);
+            if (sel_pass(v, a.min_score)) {
+                const unsigned long long k = sel_key(v);
+                if ((k & mask) == prefix) atomicAdd(&hist[(int)(k >> shift) & 255], 1);
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int need = s_need, cum = 0, b = 255;
+            for (; b >= 0; --b) {
+                if (cum + hist[b] >= need) break;
+                cum += hist[b];
+            }
+            s_bucket = b;                        // -1: fewer than `need` keys carry this prefix (only on the first pass)
+            if (b >= 0) s_need = need - cum;     // still to take from bucket b
+        }
+        __syncthreads();
+        if (s_bucket < 0) { take_all = true; break; }
+        prefix |= (unsigned long long)s_bucket << shift;
+        mask |= 0xffull << shift;
+    }
+    const int need_ties = take_all ? 0 : s_need;                 // keys equal to the threshold to take, earliest first
+    __syncthreads();
+
+    // ---- ordered gather: key > threshold always, key == threshold while the tie budget lasts (scan order) ----
+    const int64_t chunk = (int64_t)kSelThreads * kSelPerThread;
+    for (int64_t pos = 0; pos < a.L; pos += chunk) {
+        const int64_t i0 = pos + (int64_t)tid * kSelPerThread;
+        double v[kSelPerThread];
+        int cls[kSelPerThread];                                   // 0 skip, 1 take, 2 tie
+        int ties = 0;
+#pragma unroll
+        for (int j = 0; j < kSelPerThread; ++j) {
+            v[j] = (i0 + j < a.L) ? __ldg(sc + i0 + j) : -INFINITY;
+            cls[j] = 0;
+            if (sel_pass(v[j], a.min_score)) {
+                const unsigned long long k = sel_key(v[j]);
+                cls[j] = take_all ? 1 : (k > prefix ? 1 : (k == prefix ? 2 : 0));
+            }
+            ties += cls[j] == 2;
+        }
+        // exclusive prefix of the tie counts over the block (thread order = scan order)
+        int incl = ties;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int n = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += n;
+        }
+        if (lane == 31) warp_cnt[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            const int w = warp_cnt[lane];
+            int wi = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int n = __shfl_up_sync(0xffffffffu, wi, d);
+                if (lane >= d) wi += n;
+            }
+            warp_cnt[lane] = wi - w;
+            if (lane == 31) s_tot = wi;
+        }
+        __syncthreads();
+        int tie_rank = s_base + warp_cnt[wid] + (incl - ties);
+#pragma unroll
+        for (int j = 0; j < kSelPerThread; ++j) {
+            bool take = cls[j] == 1;
+            if (cls[j] == 2) { take = tie_rank < need_ties; ++tie_rank; }
+            if (take) {
+                const int o = atomicAdd(&s_fill, 1);              // any order: the sort below is a total order
+                if (o < a.Kpad) { hs[o] = v[j]; hi[o] = i0 + j; }
+            }
+        }
+        __syncthreads();
+        if (tid == 0) s_base += s_tot;
+        __syncthreads();
+    }
+    const int n_first = s_fill < K ? s_fill : K;
+
+    // ---- sort by (score desc, scan index asc) - bitonic over Kpad ----
+    for (int size = 2; size <= a.Kpad; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = tid; i < a.Kpad; i += kSelThreads) {
+                const int j = i ^ stride;
+                if (j > i) {
+                    const bool up = ((i & size) == 0);
+                    const double si = hs[i], sj = hs[j];
+                    const long long ii = hi[i], ij = hi[j];
+                    const bool j_better = sel_better(sj, ij, si, ii);
+                    if (up ? j_better : !j_better) { hs[i] = sj; hs[j] = si; hi[i] = ij; hi[j] = ii; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = tid; i < K; i += kSelThreads) {
+        const int64_t o = slot * K + i;
+        if (i < n_first) {
+            a.cand_time[o] = a.t0 + (int)(hi[i] / a.nf);
+            a.cand_freq[o] = (int)(hi[i] % a.nf);
+            a.cand_score[o] = hs[i];
+        } else {
+            a.cand_time[o] = 0; a.cand_freq[o] = 0; a.cand_score[o] = 0.0;
+        }
+    }
+    if (tid == 0) a.n_cand[slot] = n_first;
+}
+
+// ------------------------------------------------------------------------------------------
 // strips per slot the pair kernels summarise (0 when the geometry runs on sync_scores_kernel, which does not)
 int sync_tiles_per_slot(int T, int F, int s, int b) {
     int t0, nt, nf;
@@ -567,6 +707,13 @@ int select_candidates(const double *scores, int64_t n_slots, int nt, int nf, int
     a.cand_time = cand_time; a.cand_freq = cand_freq; a.cand_score = cand_score; a.n_cand = n_cand; a.n_pass = n_pass;
     a.tiles = tiles; a.n_tiles = n_tiles;
     const size_t smem = (size_t)kp * (sizeof(double) + sizeof(long long));
+    if (n_tiles < 0) {       // strict top-K (opt-in extension)
+        a.tiles = nullptr; a.n_tiles = 0;
+        FT8B_CUDA_TRY(cudaFuncSetAttribute(select_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem > 48 * 1024 ? (int)smem : 48 * 1024));
+        select_topk_kernel<<<(unsigned)n_slots, kSelThreads, smem, stream>>>(a);
+        FT8B_LAUNCH_CHECK("select_topk_kernel");
+        return 0;
+    }
     FT8B_CUDA_TRY(cudaFuncSetAttribute(select_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem > 48 * 1024 ? (int)smem : 48 * 1024));
     select_candidates_kernel<<<(unsigned)n_slots, kSelThreads, smem, stream>>>(a);
     FT8B_LAUNCH_CHECK("select_candidates_kernel");

@@ -79,9 +79,10 @@ def sync_scores(mag: torch.Tensor, time_osr: int, freq_osr: int):
     return scores, t0
 
 
-def select_candidates(scores: torch.Tensor, t0: int, K: int, min_score: float):
+def select_candidates(scores: torch.Tensor, t0: int, K: int, min_score: float, strict_topk: bool = False):
     """S2b.  scores [B, nt, nf] -> (cand_time i32 [B,K], cand_freq i32 [B,K], cand_score f64 [B,K], n_cand i32 [B],
-    n_pass i32 [B])."""
+    n_pass i32 [B]).  strict_topk (opt-in extension): the K best passers instead of the reference's list; n_pass is
+    not counted then (zeros)."""
     assert scores.is_cuda and scores.dtype == _F64 and scores.is_contiguous() and scores.dim() == 3
     B, nt, nf = scores.shape
     dev = scores.device
@@ -90,9 +91,13 @@ def select_candidates(scores: torch.Tensor, t0: int, K: int, min_score: float):
     cs = torch.zeros((B, K), dtype=_F64, device=dev)
     nc = torch.zeros((B,), dtype=torch.int32, device=dev)
     npass = torch.zeros((B,), dtype=torch.int32, device=dev)
-    _lib.check(_lib.lib().ft8b_select_candidates(_p(scores) if scores.numel() else 0, B, nt, nf, t0, K, float(min_score),
-                                                 _p(ct), _p(cf), _p(cs), _p(nc), _p(npass), _stream()),
-               "ft8b_select_candidates")
+    if strict_topk:
+        _lib.check(_lib.lib().ft8b_select_topk(_p(scores) if scores.numel() else 0, B, nt, nf, t0, K, float(min_score),
+                                               _p(ct), _p(cf), _p(cs), _p(nc), _stream()), "ft8b_select_topk")
+    else:
+        _lib.check(_lib.lib().ft8b_select_candidates(_p(scores) if scores.numel() else 0, B, nt, nf, t0, K, float(min_score),
+                                                     _p(ct), _p(cf), _p(cs), _p(nc), _p(npass), _stream()),
+                   "ft8b_select_candidates")
     return ct, cf, cs, nc, npass
 
 
@@ -247,10 +252,10 @@ class SlotDecodes:
 
 
 def make_params(sample_rate, bins_per_tone, steps_per_symbol, max_candidates, min_score, max_iterations, bin_lo, bin_hi,
-                frame_lo, frame_hi, chunk_slots=0) -> _lib.DecodeParams:
+                frame_lo, frame_hi, chunk_slots=0, flags=0) -> _lib.DecodeParams:
     return _lib.DecodeParams(float(sample_rate), int(bins_per_tone), int(steps_per_symbol), int(max_candidates),
                              int(max_iterations), float(min_score), int(bin_lo), int(bin_hi), int(frame_lo),
-                             int(frame_hi), int(chunk_slots), 0)
+                             int(frame_hi), int(chunk_slots), int(flags))
 
 
 def alloc_slot_decodes(B: int, K: int, dev, zero: bool = True) -> SlotDecodes:

@@ -80,10 +80,12 @@ def ft8_sync_score(wf: FT8Waterfall, candidate: FT8Candidate) -> float:
     return float(host[ti, candidate.abs_freq])
 
 
-def ft8_find_candidates(wf: FT8Waterfall, num_candidates: int, min_score: int) -> List[FT8Candidate]:
-    """Candidate search with the reference's exact selection semantics (ft8_decode.py:102-149)."""
+def ft8_find_candidates(wf: FT8Waterfall, num_candidates: int, min_score: int, strict_topk: bool = False) -> List[FT8Candidate]:
+    """Candidate search with the reference's exact selection semantics (ft8_decode.py:102-149).
+    strict_topk=True (opt-in extension): the num_candidates best scores instead of the reference's
+    "first K passers in scan order + one record replacement" list."""
     scores, t0, _ = _score_map(wf)
-    ct, cf, cs, nc, _ = engine.select_candidates(scores, t0, int(num_candidates), float(min_score))
+    ct, cf, cs, nc, _ = engine.select_candidates(scores, t0, int(num_candidates), float(min_score), strict_topk=strict_topk)
     n = int(nc.cpu()[0])
     ct, cf, cs = ct[0, :n].cpu().numpy(), cf[0, :n].cpu().numpy(), cs[0, :n].cpu().numpy()
     return [FT8Candidate(waterfall=wf, abs_time=int(ct[i]), abs_freq=int(cf[i]), score=float(cs[i])) for i in range(n)]
@@ -246,7 +248,8 @@ class BatchDecodes:
 
 def decode_slots(waves, sample_rate, bins_per_tone: int = 2, steps_per_symbol: int = 2, max_candidates: int = 20,
                  min_score=10, max_iterations: int = 20, freq_min=None, freq_max=None, time_min=None, time_max=None,
-                 chunk_slots: int = 0, return_device: bool = False, piece_slots: int = 128, pcm16: bool = False):
+                 chunk_slots: int = 0, return_device: bool = False, piece_slots: int = 128, pcm16: bool = False,
+                 strict_topk: bool = False):
     """Decode a batch of equal-length slots: waves [B, N] (NumPy or torch, host or device, float32/float64).
 
     With pcm16=True an int16 array is taken as PCM and normalised on the GPU as float32(x)/32767, the way the
@@ -254,7 +257,9 @@ def decode_slots(waves, sample_rate, bins_per_tone: int = 2, steps_per_symbol: i
     bytes of float32.  Without it integers are converted to float64 unscaled, as the reference would treat them.
     Per-slot semantics are exactly decode_ft8_message's.  Host input is copied to the GPU inside this
     call (pinned torch tensors copy asynchronously); results come back as a BatchDecodes (host) or, with
-    return_device=True, as the engine.SlotDecodes device tensors."""
+    return_device=True, as the engine.SlotDecodes device tensors.
+    strict_topk=True (opt-in extension, not the reference's behaviour): every slot's candidate list is its
+    max_candidates best sync scores instead of the reference's scan-order list (ft8_decode.py:127-140)."""
     dev = engine.require_cuda()
     if isinstance(waves, np.ndarray):
         if np.iscomplexobj(waves):
@@ -270,7 +275,8 @@ def decode_slots(waves, sample_rate, bins_per_tone: int = 2, steps_per_symbol: i
     B, N = waves.shape
     g = decode_geometry(N, sample_rate, bins_per_tone, steps_per_symbol, freq_min, freq_max, time_min, time_max)
     params = engine.make_params(sample_rate, bins_per_tone, steps_per_symbol, max_candidates, min_score, max_iterations,
-                                g["bin_lo"], g["bin_hi"], g["frame_lo"], g["frame_hi"], chunk_slots)
+                                g["bin_lo"], g["bin_hi"], g["frame_lo"], g["frame_hi"], chunk_slots,
+                                flags=_lib.FLAG_STRICT_TOPK if strict_topk else 0)
     if max_candidates > _lib.MAX_CANDIDATES:
         raise NotImplementedError("max_candidates=%d exceeds the kernel limit %d" % (max_candidates, _lib.MAX_CANDIDATES))
     if B == 0 or g["T_all"] <= 0:
@@ -337,17 +343,18 @@ def decode_slots_drift(waves, sample_rate, drift_hz_per_s, bins_per_tone: int = 
 
 def decode_ft8_message(wave_data: np.ndarray, sample_rate: int, bins_per_tone: int = 2, steps_per_symbol: int = 2,
                        max_candidates: int = 20, min_score: int = 10, max_iterations: int = 20,
-                       freq_min: float = None, freq_max: float = None, time_min: float = None, time_max: float = None
-                       ) -> List[Tuple[FT8Message, FT8DecodeStatus, float, float, float]]:
+                       freq_min: float = None, freq_max: float = None, time_min: float = None, time_max: float = None,
+                       strict_topk: bool = False) -> List[Tuple[FT8Message, FT8DecodeStatus, float, float, float]]:
     """Decode one waveform (ft8_decode.py:288-394).  Returns the reference's list of
     (FT8Message, FT8DecodeStatus, time_sec, freq_hz, score) in candidate (score-descending) order, with
-    time_sec = abs_time / sample_rate and freq_hz = abs_freq / bins_per_tone * 6.25 as the reference defines them."""
+    time_sec = abs_time / sample_rate and freq_hz = abs_freq / bins_per_tone * 6.25 as the reference defines them.
+    strict_topk is the one extra keyword (default off = the reference's candidate list), see decode_slots."""
     x = _as_real_audio(wave_data)
     nperseg, _, _ = _lib.plan(sample_rate, bins_per_tone, steps_per_symbol)
     if len(x) < nperseg:
         return []
     return decode_slots(x.reshape(1, -1), sample_rate, bins_per_tone, steps_per_symbol, max_candidates, min_score,
-                        max_iterations, freq_min, freq_max, time_min, time_max)[0]
+                        max_iterations, freq_min, freq_max, time_min, time_max, strict_topk=strict_topk)[0]
 
 
 __all__ = [

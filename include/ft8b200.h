@@ -53,6 +53,7 @@ extern "C" {
 
 #define FT8B_LDPC_N 174
 #define FT8B_LDPC_M 83
+#define FT8B_FLAG_STRICT_TOPK 1    /* ft8b_decode_params.flags: candidate list = the K best scores (ft8b_select_topk) */
 #define FT8B_MAX_CANDIDATES 4096   /* K limit of ft8b_select_candidates */
 
 int ft8b_version(void);
@@ -100,6 +101,14 @@ int ft8b_sync_scores(const double *mag, int64_t n_slots, int T, int F, int time_
 int ft8b_select_candidates(const double *scores, int64_t n_slots, int nt, int nf, int t0, int K, double min_score,
                            int32_t *cand_time, int32_t *cand_freq, double *cand_score, int32_t *n_cand,
                            int32_t *n_pass, void *stream);
+/*
+ * OPT-IN EXTENSION (not the reference's behaviour; SURVEY Appendix D "may add an opt-in strict top-K"): the K best
+ * threshold passers by (score descending, scan position ascending), in that order - what a reader of
+ * ft8_find_candidates would expect it to return.  Same outputs as ft8b_select_candidates.  In the pipeline it is
+ * chosen with FT8B_FLAG_STRICT_TOPK in ft8b_decode_params.flags; the default stays the reference's list.
+ */
+int ft8b_select_topk(const double *scores, int64_t n_slots, int nt, int nf, int t0, int K, double min_score,
+                     int32_t *cand_time, int32_t *cand_freq, double *cand_score, int32_t *n_cand, void *stream);
 
 /*
  * S3  ft8_decode_candidate (ft8_decode.py:225-273) for every candidate of every slot:
@@ -203,7 +212,7 @@ typedef struct {
     int32_t bin_lo, bin_hi;       /* rows kept (freq_min/freq_max mask), within [0, ceil(nfft/2)] */
     int64_t frame_lo, frame_hi;   /* columns kept (time_min/time_max mask) */
     int32_t chunk_slots;          /* 0 = library default */
-    int32_t reserved;
+    int32_t flags;                /* 0 = the reference's behaviour; FT8B_FLAG_* bits opt in to extensions */
 } ft8b_decode_params;
 
 int64_t ft8b_decode_workspace_bytes(const ft8b_decode_params *p, int64_t n_slots, int64_t n_samples);

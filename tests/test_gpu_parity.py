@@ -799,3 +799,76 @@ def test_non_finite_audio_is_contained():
     assert len(alone[0]) >= 1 and mixed[0] == alone[0] and mixed[2] == alone[1]
     assert mixed[4] == []                               # all-NaN audio: nothing passes, nothing decodes
     assert not mixed.arrays.ok[4].any()
+
+
+# ------------------------------------------------------------------------------------------ opt-in strict top-K
+def _numpy_topk(score_map, t0, K, thr):
+    """The K best passers by (score descending, scan position ascending) - plain NumPy statement of ft8b_select_topk."""
+    flat = score_map.reshape(-1)
+    ok = np.isfinite(flat) | (flat == np.inf)
+    ok &= ~(flat < thr) & ~np.isnan(flat) & (flat != -np.inf)
+    idx = np.flatnonzero(ok)
+    order = idx[np.lexsort((idx, -(flat[idx] + 0.0)))][:K]
+    nf = score_map.shape[1]
+    return [(t0 + int(i) // nf, int(i) % nf, float(flat[i])) for i in order]
+
+
+@pytest.mark.parametrize("nt,nf,K,thr,levels", [
+    (88, 1906, 20, 1.0, 0), (88, 1906, 1, 1.0, 0), (88, 1906, 300, 3.0, 0), (88, 1906, 4096, -1e9, 0),
+    (88, 1906, 2000, 0.0, 7),        # seven distinct values only: the tie budget decides almost everything
+    (5, 40, 64, 0.5, 3),             # fewer passers than K
+    (44, 947, 257, 2.0, 1000),
+])
+def test_strict_topk_selection_vs_numpy(nt, nf, K, thr, levels):
+    """EXTENSION (opt-in): ft8b_select_topk returns the K best passers, ties by scan position."""
+    g = torch.Generator(device="cuda").manual_seed(nt * nf + K)
+    sc = torch.randn((4, nt, nf), generator=g, device="cuda", dtype=torch.float64) * 4.0
+    if levels:
+        sc = torch.round(sc * levels / 8.0) * (8.0 / levels) + 0.0
+    sc[1, 0, :7] = float("-inf")
+    sc[1, nt // 2, 3] = float("nan")
+    sc[2, nt - 1, nf - 1] = float("inf")
+    sc[3] = -0.0                                             # one value everywhere (and the sign of zero must not matter)
+    sc[3, 1, 5] = 0.0
+    ct, cf, cs, nc, _ = engine.select_candidates(sc.contiguous(), -20, K, thr, strict_topk=True)
+    host = sc.cpu().numpy()
+    for b in range(4):
+        want = _numpy_topk(host[b], -20, K, thr)
+        n = int(nc[b])
+        assert n == len(want), (b, n, len(want))
+        got = list(zip(ct[b, :n].tolist(), cf[b, :n].tolist(), cs[b, :n].tolist()))
+        assert got == want, (b, [(i, x, y) for i, (x, y) in enumerate(zip(got, want)) if x != y][:3])
+
+
+def test_strict_topk_pipeline(c1_slot):
+    """decode_slots(strict_topk=True): the candidate list is the K best sync scores of the slot's score map,
+    the default list is untouched, and a dense band decodes with K = 20."""
+    kw = dict(bins_per_tone=2, steps_per_symbol=2, max_candidates=20, min_score=1, max_iterations=20)
+    x = c1_slot.astype(np.float32).reshape(1, -1)
+    ref = fd.decode_slots(x, 12000, **kw)
+    strict = fd.decode_slots(x, 12000, strict_topk=True, **kw)
+    a, b = ref.arrays, strict.arrays
+    assert int(b.n_cand[0]) == 20
+    assert (int(a.cand_time[0, 0]), int(a.cand_freq[0, 0])) == (int(b.cand_time[0, 0]), int(b.cand_freq[0, 0])) == (8, 161)
+    assert (a.cand_time[0, 1:] == -20).all()                                   # the reference's list: untouched
+    assert bytes(strict[0][0][0].payload) == synth.C1_PAYLOAD
+    s = b.cand_score[0].numpy()
+    assert (np.diff(s) <= 0).all()
+    # stage by stage: same list from the stand-alone kernel on the same score map
+    g = fd.decode_geometry(x.shape[1], 12000, 2, 2, None, None, None, None)
+    mag = engine.stft_db(torch.from_numpy(x).cuda(), g["nperseg"], g["hop"], g["nfft"], g["bin_lo"], g["bin_hi"], g["frame_lo"], g["frame_hi"])
+    sc, t0 = engine.sync_scores(mag, 2, 2)
+    ct, cf, cs, nc, _ = engine.select_candidates(sc, t0, 20, 1.0, strict_topk=True)
+    assert torch.equal(ct.cpu(), b.cand_time) and torch.equal(cf.cpu(), b.cand_freq) and torch.equal(cs.cpu(), b.cand_score)
+    want = _numpy_topk(sc[0].cpu().numpy(), t0, 20, 1.0)
+    assert list(zip(b.cand_time[0].tolist(), b.cand_freq[0].tolist(), b.cand_score[0].tolist())) == want
+    # device-resident input and the one-slot drop-in call take the same flag
+    dev_in = fd.decode_slots(torch.from_numpy(x).cuda(), 12000, strict_topk=True, return_device=True, **kw)
+    assert torch.equal(dev_in.cand_freq.cpu(), b.cand_freq)
+    assert [bytes(m.payload) for m, *_ in fd.decode_ft8_message(c1_slot, 12000, strict_topk=True, **kw)] == \
+           [bytes(m.payload) for m, *_ in strict[0]]
+    c2, payloads, *_ = synth.c2_slot()
+    kw2 = dict(kw, min_score=3, freq_max=3100.0)
+    assert fd.decode_ft8_message(c2, 12000, **kw2) == []                       # the reference's quirk: 20 noise cells
+    found = {bytes(m.payload) for m, *_ in fd.decode_ft8_message(c2, 12000, strict_topk=True, **kw2)}
+    assert len(found & {bytes(p) for p in payloads}) >= 1
