@@ -9,7 +9,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from conftest import load_golden
+from conftest import ROOT, load_golden
 from ft8_demodulator_b200 import dist as fdist, synth
 from ft8_demodulator_b200.ft8_demodulator import constants, crc, ft8_decode as fd, ftx_types, spectrogram_analyse as sa
 
@@ -228,3 +228,17 @@ def test_dedupe_keeps_first_occurrence():
     assert [r[4] for r in out] == [9.0, 8.0]
     assert [x[0] for x in pp.annotate(res)] == ["CQ K1ABC FN42", "HELLO"]
     assert len(pp.annotate(res, unique=False)) == 5
+
+
+def test_decode_params_flags_layout():
+    """ft8b_decode_params as ctypes: 64 bytes, `flags` last (0 = the reference's behaviour), FT8B_FLAG_STRICT_TOPK = 1
+    as the header says."""
+    import ctypes as C
+    import re
+    from ft8_demodulator_b200 import _lib, engine
+    p = engine.make_params(12000, 2, 2, 20, 1, 20, 0, 1920, 0, 186)
+    assert p.flags == 0 and C.sizeof(p) == 64
+    q = engine.make_params(12000, 2, 2, 20, 1, 20, 0, 1920, 0, 186, flags=_lib.FLAG_STRICT_TOPK)
+    assert q.flags == 1 and _lib.DecodeParams.flags.offset == 60
+    hdr = open(os.path.join(ROOT, "include", "ft8b200.h")).read()
+    assert int(re.search(r"#define FT8B_FLAG_STRICT_TOPK (\d+)", hdr).group(1)) == _lib.FLAG_STRICT_TOPK
