@@ -296,14 +296,15 @@ def decode_slots(waves, sample_rate, bins_per_tone: int = 2, steps_per_symbol: i
 
 def decode_slots_drift(waves, sample_rate, drift_hz_per_s, bins_per_tone: int = 2, steps_per_symbol: int = 2,
                        max_candidates: int = 20, min_score=10, max_iterations: int = 20, freq_min=None, freq_max=None,
-                       time_min=None, time_max=None, slots_per_pass: int = 256):
+                       time_min=None, time_max=None, slots_per_pass: int = 256, strict_topk: bool = False):
     """EXTENSION (not in the reference; BASELINE north_star's drift-hypothesis sync for the satellite path):
     decode_slots with a Costas search over linear Doppler-drift hypotheses.
 
     `drift_hz_per_s` lists the hypotheses; 0.0 is always tried first, so a drift-free signal decodes exactly as in
     decode_slots (with drift_hz_per_s=[0.0] the two functions return identical results).  For hypothesis r the tone
     grid of symbol q of a candidate is shifted by round(r * 0.16 s * q / bin_width) bins, both in the sync score and
-    in the LLR extraction.  Returns (BatchDecodes, drift_hz_per_s of every candidate as float64 [B, K])."""
+    in the LLR extraction.  strict_topk as in decode_slots (the K best scores instead of the reference's scan-order
+    list).  Returns (BatchDecodes, drift_hz_per_s of every candidate as float64 [B, K])."""
     dev = engine.require_cuda()
     waves = waves if isinstance(waves, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(np.asarray(waves)))
     if waves.dim() == 1:
@@ -328,7 +329,7 @@ def decode_slots_drift(waves, sample_rate, drift_hz_per_s, bins_per_tone: int = 
             score, hyp, t0 = engine.sync_scores_drift(mag, steps_per_symbol, bins_per_tone, d_bins)
             if score.numel() == 0:
                 continue
-            ct, cf, cs, nc, _ = engine.select_candidates(score, t0, K, float(min_score))
+            ct, cf, cs, nc, _ = engine.select_candidates(score, t0, K, float(min_score), strict_topk=strict_topk)
             live = torch.arange(K, device=dev)[None, :] < nc[:, None]
             ti = torch.where(live, ct - t0, torch.zeros_like(ct)).long()
             h = hyp[torch.arange(hi - lo, device=dev)[:, None], ti, cf.long()].long()      # hypothesis of each candidate

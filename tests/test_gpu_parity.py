@@ -867,6 +867,10 @@ def test_strict_topk_pipeline(c1_slot):
     assert torch.equal(dev_in.cand_freq.cpu(), b.cand_freq)
     assert [bytes(m.payload) for m, *_ in fd.decode_ft8_message(c1_slot, 12000, strict_topk=True, **kw)] == \
            [bytes(m.payload) for m, *_ in strict[0]]
+    # the drift-hypothesis path takes the flag too: with the single hypothesis 0 Hz/s it is the plain strict pipeline
+    dr, _ = fd.decode_slots_drift(x, 12000, [0.0], strict_topk=True, **kw)
+    assert torch.equal(dr.arrays.cand_time, b.cand_time) and torch.equal(dr.arrays.cand_freq, b.cand_freq)
+    assert torch.equal(dr.arrays.ok, b.ok) and torch.equal(dr.arrays.payload, b.payload)
     c2, payloads, *_ = synth.c2_slot()
     kw2 = dict(kw, min_score=3, freq_max=3100.0)
     assert fd.decode_ft8_message(c2, 12000, **kw2) == []                       # the reference's quirk: 20 noise cells
