@@ -242,3 +242,32 @@ def test_decode_params_flags_layout():
     assert q.flags == 1 and _lib.DecodeParams.flags.offset == 60
     hdr = open(os.path.join(ROOT, "include", "ft8b200.h")).read()
     assert int(re.search(r"#define FT8B_FLAG_STRICT_TOPK (\d+)", hdr).group(1)) == _lib.FLAG_STRICT_TOPK
+
+
+def test_batch_decodes_materialisation():
+    """BatchDecodes builds the reference's 5-tuples (ft8_decode.py:383-391) from the packed arrays: successes only, in
+    candidate order, candidates beyond n_cand ignored; indexing, negative indices, iteration and to_lists agree."""
+    from ft8_demodulator_b200 import engine
+    out = engine.alloc_slot_decodes(3, 6, torch.device("cpu"))
+    out.n_cand[:] = torch.tensor([6, 2, 0])
+    out.ok[0, 1] = 1; out.ok[0, 4] = 1; out.ok[1, 0] = 1
+    out.ok[1, 3] = 1                                   # beyond n_cand[1] = 2: not a candidate of this slot
+    out.payload[0, 1] = torch.arange(10, dtype=torch.uint8)
+    out.payload[0, 4] = torch.arange(10, 20, dtype=torch.uint8)
+    out.crc_calculated[0, 1] = 7997; out.crc_extracted[0, 1] = 7997; out.ldpc_errors[0, 4] = 0
+    out.cand_time[0, 1] = 8; out.cand_freq[0, 1] = 161; out.cand_score[0, 1] = 10.5
+    out.cand_time[0, 4] = -20; out.cand_freq[0, 4] = 30; out.cand_score[0, 4] = 2.25
+    b = fd.BatchDecodes(out, 12000, 2)
+    assert len(b) == 3
+    r0 = b[0]
+    assert [bytes(m.payload) for m, *_ in r0] == [bytes(range(10)), bytes(range(10, 20))]
+    m, st, t, f, sc = r0[0]
+    assert isinstance(m, ftx_types.FT8Message) and isinstance(m.payload, bytearray) and m.hash == 7997
+    assert isinstance(st, ftx_types.FT8DecodeStatus) and (st.ldpc_errors, st.crc_extracted, st.crc_calculated) == (0, 7997, 7997)
+    assert (t, f, sc) == (8 / 12000, 161 / 2 * 6.25, 10.5)
+    assert r0[1][2:] == (-20 / 12000, 30 / 2 * 6.25, 2.25)
+    assert len(b[1]) == 1 and b[2] == [] and b[-1] == [] and b[-3] == r0
+    assert [len(x) for x in b] == [2, 1, 0] and b.to_lists() == [b[0], b[1], b[2]]
+    with pytest.raises(IndexError):
+        b[3]
+    assert b.payload_sets()[0] == {bytes(range(10)), bytes(range(10, 20))}
