@@ -21,6 +21,7 @@ of the same workload.
 """
 import argparse
 import ctypes as C
+import gc
 import json
 import os
 import subprocess
@@ -327,6 +328,8 @@ def main():
         for _ in range(2):
             res = fd.decode_slots(host, FS, chunk_slots=args.chunk, **kw)
         barrier()
+        gc.collect()
+        gc.disable()        # a generational collection inside three 55-ms host calls reads as a 10 % outlier
         t0 = time.perf_counter()
         dt_dev = 0.0
         e2e_steps = max(2, min(args.steps, 3))
@@ -334,6 +337,7 @@ def main():
             res = fd.decode_slots(host, FS, chunk_slots=args.chunk, **kw)
             dt_dev += engine._lib.lib().ft8b_last_host_call_ms() * 1e-3
         dt = time.perf_counter() - t0
+        gc.enable()
 
         def timed(fn, n=2):
             fn()
