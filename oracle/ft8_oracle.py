@@ -130,6 +130,67 @@ def score_map(mag, tosr, fosr):
     return out
 
 
+def score_map_drift(mag, tosr, fosr, drift_bins_per_symbol):
+    """CPU statement of the drift-hypothesis Costas search (an EXTENSION of the new repo: BASELINE north_star names it
+    for the satellite path, the reference has no counterpart - parity unpinned; with the single hypothesis 0.0 it is
+    ft8_sync_score's map, ft8_decode.py:47-100, which is what pins this function).
+
+    For hypothesis d the tone grid of symbol q (counted from the candidate's first symbol) is shifted by
+    round-half-even(d * q) bins.  A hypothesis is scored with the reference's running sum over the shifted cells; cells
+    whose symbol or bins leave the waterfall are skipped.  Every (abs_time, abs_freq) gets the best score over the
+    hypotheses (first maximum wins) and that hypothesis' index.  NumPy, vectorised over frequency only: every map
+    entry sees the reference's sequence of additions.  mag [F, T] as elsewhere in this module.
+    Returns (best [nt, nf] float64, hyp [nt, nf] int32)."""
+    m = _f64(mag)
+    F, T = m.shape
+    t0, t1, f0, f1 = search_ranges(F, T, tosr, fosr)
+    nt, nf = max(t1 - t0, 0), max(f1 - f0, 0)
+    best = np.full((nt, nf), -np.inf)
+    hyp = np.zeros((nt, nf), dtype=np.int32)
+    if nt == 0 or nf == 0:
+        return best, hyp
+    costas = [3, 1, 4, 0, 6, 5, 2]
+    nb = T // tosr
+    f = np.arange(f0, f1)
+    for ti in range(nt):
+        at = t0 + ti
+        base = at // tosr                                   # Python floor division, as the reference's block index
+        for h, d in enumerate(drift_bins_per_symbol):
+            score = np.zeros(nf)
+            num = np.zeros(nf, dtype=np.int64)
+            for blk_i in range(3):
+                for k in range(7):
+                    q = blk_i * 36 + k
+                    blk = base + q
+                    if blk < 0 or blk >= nb:
+                        continue
+                    tone = costas[k]
+                    bins = f + int(np.rint(d * q)) + tone * fosr
+                    ok = (bins - (fosr if tone > 0 else 0) >= 0) & (bins + fosr < F)
+                    bi = np.where(ok, bins, fosr)                               # any valid index where masked out
+                    col = at + q * tosr
+                    p = m[bi, col]
+
+                    def add(term, cond):
+                        nonlocal score, num
+                        score = np.where(cond, score + term, score)
+                        num = num + cond
+
+                    if tone > 0:
+                        add(p - m[bi - fosr, col], ok)
+                    add(p - m[bi + fosr, col], ok)
+                    if k > 0 and blk > 0:
+                        add(p - m[bi, col - tosr], ok)
+                    if k < 6 and blk + 1 < nb:
+                        add(p - m[bi, col + tosr], ok)
+            with np.errstate(invalid="ignore", divide="ignore"):
+                v = np.where((num == 0) | ~np.isfinite(score), -np.inf, score / np.maximum(num, 1))
+            better = v > best[ti]
+            best[ti] = np.where(better, v, best[ti])
+            hyp[ti] = np.where(better, h, hyp[ti])
+    return best, hyp
+
+
 def ft8_find_candidates(mag, tosr, fosr, num_candidates, min_score):
     """Returns (abs_time[int32], abs_freq[int32], score[f64], n_passers).  Raises TypeError on a heap tie."""
     m = _f64(mag)

@@ -876,3 +876,27 @@ def test_strict_topk_pipeline(c1_slot):
     assert fd.decode_ft8_message(c2, 12000, **kw2) == []                       # the reference's quirk: 20 noise cells
     found = {bytes(m.payload) for m, *_ in fd.decode_ft8_message(c2, 12000, strict_topk=True, **kw2)}
     assert len(found & {bytes(p) for p in payloads}) >= 1
+
+
+@pytest.mark.parametrize("F,T,s,b,hyps", [
+    (300, 190, 3, 1, [0.0, 0.4, -0.4, 0.123]),
+    (101, 200, 2, 2, [0.0, 0.17, -0.17]),
+    (400, 186, 1, 2, [0.0] + list(np.linspace(-0.2, 0.2, 9))),
+])
+def test_drift_sync_vs_cpu_statement(orc, F, T, s, b, hyps):
+    """The drift-hypothesis sync kernels against the CPU statement oracle/ft8_oracle.py::score_map_drift (itself pinned
+    by the reference's plain score map at the single hypothesis 0): the direct kernel performs the same additions in
+    the same order, the tiled kernels the same contrasts in another association."""
+    from ft8_demodulator_b200 import _lib
+    rng = np.random.default_rng(F * 3 + T)
+    mag = rng.standard_normal((F, T)) * 6 - 60
+    ref, ref_h = orc.score_map_drift(mag, s, b, hyps)
+    m = engine._dev(np.ascontiguousarray(mag.T).reshape(1, T, F))
+    for variant in (_lib.DRIFT_DIRECT, _lib.DRIFT_AUTO):
+        got, hyp, t0 = engine.sync_scores_drift(m, s, b, hyps, variant=variant)
+        g, h = got[0].cpu().numpy(), hyp[0].cpu().numpy()
+        assert g.shape == ref.shape and t0 == -10 * s
+        assert np.array_equal(np.isneginf(g), np.isneginf(ref))
+        fin = np.isfinite(ref)
+        assert np.abs(g[fin] - ref[fin]).max() < 1e-12
+        assert (h != ref_h).mean() < 1e-3          # another winner only between hypotheses that tie to rounding

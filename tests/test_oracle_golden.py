@@ -137,3 +137,18 @@ def test_other_rates(orc, tag):
     stride = max(1, mag.shape[0] // 12)
     assert np.abs(mag[::stride] - g[tag + "__spec_rows_stride"]).max() < SPEC_TOL_DB
     assert bytes(pl) in [bytes(p) for p in gold["res_payload"]]
+
+
+@pytest.mark.parametrize("F,T,s,b", [(300, 190, 3, 1), (101, 200, 2, 2), (64, 120, 2, 4), (400, 186, 1, 2)])
+def test_drift_statement_is_pinned_by_the_plain_score_map(orc, F, T, s, b):
+    """The NumPy statement of the drift-hypothesis search (an extension, no reference counterpart) with the single
+    hypothesis 0 is the reference's ft8_sync_score map (ft8_decode.py:47-100) bit for bit - the C restatement of that
+    map is what the golden fixtures pin; more hypotheses can only raise a score."""
+    rng = np.random.default_rng(F + T)
+    mag = rng.standard_normal((F, T)) * 6 - 60
+    ref = orc.score_map(mag, s, b)
+    got, hyp = orc.score_map_drift(mag, s, b, [0.0])
+    assert np.array_equal(got, ref) and not hyp.any()
+    g3, h3 = orc.score_map_drift(mag, s, b, [0.0, 0.21, -0.21])
+    assert (g3 >= ref).all() and set(np.unique(h3)) <= {0, 1, 2}
+    assert np.array_equal(g3[h3 == 0], ref[h3 == 0])
