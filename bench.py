@@ -57,6 +57,13 @@ SURVEY_FP32_BYTES = {"stft_db": 180000 * 4 + 1920 * 186 * 4, "costas_sync": 1920
 STAGES = ["stft_db", "costas_sync", "select", "llr", "ldpc_crc"]
 
 
+def workload_config(slots, chunk):
+    """`config` of the JSON line - the same object on both arms (the reference arm runs a bounded sample of this
+    workload; the sample is described in its cpu_baseline)."""
+    return {"workload": WORKLOAD % slots, "slots_per_gpu": slots, "l2_policy": "inputs (2.95 GB/GPU) larger than L2, no flush",
+            "chunk_slots": chunk or "library default", "sharding": "slots split across ranks, no collective"}
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -235,8 +242,9 @@ def reference_arm(args):
         "impl": "reference", "metric": "decoded 15-s FT8 slots/sec", "value": val, "unit": "slots/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD % args.slots, "cpu_sample_slots_per_step": sample},
+        "config": workload_config(args.slots, args.chunk),
         "cpu_baseline": {"value": val, "unit": "slots/s", "cores": threads, "kind": "port",
+                         "sample_slots_per_step": sample,
                          "sample": "%d C3 slots per step through oracle/ft8_oracle.c (compiled C restatement of the "
                                    "reference's Python path; the Python reference itself measured 0.064 slots/s per core "
                                    "in the build container, BASELINE.md section 2)" % sample},
@@ -470,8 +478,7 @@ def main():
         "metric": "decoded 15-s FT8 slots/sec", "value": value, "unit": "slots/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD % B, "slots_per_gpu": B, "l2_policy": "inputs (2.95 GB/GPU) larger than L2, no flush",
-                   "chunk_slots": args.chunk or "library default", "sharding": "slots split across ranks, no collective"},
+        "config": workload_config(B, args.chunk),
         "candidates_per_s": value * 88 * 1906, "ldpc_codewords_per_s": world * n_words / (ms_step * 1e-3),
         "roofline": roof, "stages": stages, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
         "clocks": clocks, "decode_check": {"slots_with_tx_payload_decoded": hit, "slots": B}, "parity": parity,

@@ -24,7 +24,7 @@ int release_plans();
 int sync_tiles_per_slot(int, int, int, int);
 int sync_scores(const double *, int64_t, int, int, int, int, double *, SyncTile *, cudaStream_t);
 int select_candidates(const double *, int64_t, int, int, int, int, double, int32_t *, int32_t *, double *, int32_t *,
-                      int32_t *, const SyncTile *, int, cudaStream_t);
+                      int32_t *, const SyncTile *, int, const double *, int, int, int, int, cudaStream_t);
 int decode_candidates(const double *, int64_t, int, int, int, int, const int32_t *, const int32_t *, const int32_t *, int,
                       int, uint8_t *, int32_t *, int32_t *, int32_t *, uint8_t *, double *, uint8_t *, const double *,
                       cudaStream_t);
@@ -187,14 +187,25 @@ int ft8b_select_candidates(const double *scores, int64_t n_slots, int nt, int nf
                            int32_t *cand_time, int32_t *cand_freq, double *cand_score, int32_t *n_cand, int32_t *n_pass,
                            void *stream) {
     return select_candidates(scores, n_slots, nt, nf, t0, K, min_score, cand_time, cand_freq, cand_score, n_cand, n_pass,
-                             nullptr, 0, (cudaStream_t)stream);
+                             nullptr, 0, nullptr, 0, 0, 0, 0, (cudaStream_t)stream);
+}
+
+int ft8b_find_candidates(const double *mag, const double *scores, int64_t n_slots, int T, int F, int s, int b, int K,
+                         double min_score, int32_t *cand_time, int32_t *cand_freq, double *cand_score, int32_t *n_cand,
+                         int32_t *n_pass, void *stream) {
+    if (!mag) FT8B_ARG_FAIL("ft8b_find_candidates: null spectrogram");
+    if (T < 0 || F < 0 || s < 1 || b < 1) FT8B_ARG_FAIL("ft8b_find_candidates: bad shape");
+    int t0, nt, nf;
+    ft8b_search_ranges(T, F, s, b, &t0, &nt, &nf);
+    return select_candidates(scores, n_slots, nt, nf, t0, K, min_score, cand_time, cand_freq, cand_score, n_cand, n_pass,
+                             nullptr, 0, mag, T, F, s, b, (cudaStream_t)stream);
 }
 
 int ft8b_select_topk(const double *scores, int64_t n_slots, int nt, int nf, int t0, int K, double min_score,
                      int32_t *cand_time, int32_t *cand_freq, double *cand_score, int32_t *n_cand, void *stream) {
     // n_tiles = -1 selects the strict top-K kernel
     return select_candidates(scores, n_slots, nt, nf, t0, K, min_score, cand_time, cand_freq, cand_score, n_cand, nullptr,
-                             nullptr, -1, (cudaStream_t)stream);
+                             nullptr, -1, nullptr, 0, 0, 0, 0, (cudaStream_t)stream);
 }
 
 int ft8b_decode_candidates(const double *mag, int64_t n_slots, int T, int F, int s, int b, const int32_t *cand_time,
@@ -264,6 +275,7 @@ int ft8b_dechirp(const void *in, int in_dtype, int64_t n, double c2, double c3, 
 struct ChunkPlan {
     int64_t per_slot;   // bytes
     int chunk, n_tiles;
+    int64_t limit;      // min(chunk limit, n_slots): no batch of <= n_slots slots runs a larger chunk
 };
 static ChunkPlan chunk_plan(const ft8b_decode_params *p, const Geometry &g, int64_t n_slots) {
     ChunkPlan c;
@@ -272,6 +284,7 @@ static ChunkPlan chunk_plan(const ft8b_decode_params *p, const Geometry &g, int6
     const int64_t n = n_slots > 0 ? n_slots : 1;
     int64_t lim = p->chunk_slots > 0 ? p->chunk_slots : default_chunk_slots(c.per_slot);
     if (lim > n) lim = n;
+    c.limit = lim;
     const int64_t n_chunks = (n + lim - 1) / lim;
     c.chunk = (int)((n + n_chunks - 1) / n_chunks);
     return c;
@@ -282,8 +295,13 @@ int64_t ft8b_decode_workspace_bytes(const ft8b_decode_params *p, int64_t n_slots
     Geometry g;
     if (geometry(p, n_samples, &g)) return FT8B_ERR_ARG;
     const ChunkPlan c = chunk_plan(p, g, n_slots);
-    // chunk spectrogram + score map + strip summaries, then the LLR vectors of every candidate of the batch
-    return c.per_slot * c.chunk + 8ll * kLdpcN * p->max_candidates * (n_slots > 0 ? n_slots : 0) + 256;
+    // Chunk spectrogram + score map + strip summaries, then the LLR vectors of every candidate of the batch.
+    // The chunk term is sized for the LARGEST chunk any batch of at most n_slots slots can be cut into
+    // (min(limit, n_slots) slots), not for the balanced chunk of exactly n_slots: a workspace sized for n_slots
+    // therefore also serves every shorter batch decoded with the same parameters (the tail piece of
+    // ft8b_decode_slots_host: 128-slot pieces with chunk_slots = 100 run as 2 x 64, a 72..100-slot tail as one chunk).
+    const int64_t n = n_slots > 0 ? n_slots : 0;
+    return c.per_slot * (c.limit < 1 ? 1 : c.limit) + 8ll * kLdpcN * p->max_candidates * n + 256;
 }
 
 int ft8b_decode_slots(const void *wave, int wave_dtype, int64_t n_slots, int64_t n_samples, int64_t slot_stride,
@@ -291,6 +309,7 @@ int ft8b_decode_slots(const void *wave, int wave_dtype, int64_t n_slots, int64_t
                       int32_t *cand_freq, double *cand_score, int32_t *n_cand, uint8_t *ok, int32_t *ldpc_errors,
                       int32_t *crc_extracted, int32_t *crc_calculated, uint8_t *payload, void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
+    // crc_extracted / crc_calculated may be NULL (not wanted); every other array is required
     if (!p || !wave || !workspace || !cand_time || !cand_freq || !cand_score || !n_cand || !ok || !ldpc_errors || !payload)
         FT8B_ARG_FAIL("ft8b_decode_slots: null pointer");
     if (wave_dtype != FT8B_DTYPE_F32 && wave_dtype != FT8B_DTYPE_F64 && wave_dtype != FT8B_DTYPE_I16) FT8B_ARG_FAIL("ft8b_decode_slots: bad dtype");
@@ -305,11 +324,19 @@ int ft8b_decode_slots(const void *wave, int wave_dtype, int64_t n_slots, int64_t
     const int K = p->max_candidates;
     const size_t elt = wave_dtype == FT8B_DTYPE_F32 ? 4 : (wave_dtype == FT8B_DTYPE_I16 ? 2 : 8);
     if (g.T <= 0 || g.F <= 0 || g.score_elems == 0 || K == 0) {
-        // nothing to search: the reference returns an empty list
+        // nothing to search: the reference returns an empty list.  Every output array is defined (zeros), as after a
+        // search that found nothing - a direct C caller may pass uninitialised buffers.
+        const size_t nK = (size_t)n_slots * (size_t)K;
         FT8B_CUDA_TRY(cudaMemsetAsync(n_cand, 0, sizeof(int32_t) * n_slots, stream));
-        if (K > 0) {
-            FT8B_CUDA_TRY(cudaMemsetAsync(ok, 0, (size_t)n_slots * K, stream));
-            FT8B_CUDA_TRY(cudaMemsetAsync(ldpc_errors, 0, sizeof(int32_t) * (size_t)n_slots * K, stream));
+        if (nK > 0) {
+            FT8B_CUDA_TRY(cudaMemsetAsync(cand_time, 0, sizeof(int32_t) * nK, stream));
+            FT8B_CUDA_TRY(cudaMemsetAsync(cand_freq, 0, sizeof(int32_t) * nK, stream));
+            FT8B_CUDA_TRY(cudaMemsetAsync(cand_score, 0, sizeof(double) * nK, stream));
+            FT8B_CUDA_TRY(cudaMemsetAsync(ok, 0, nK, stream));
+            FT8B_CUDA_TRY(cudaMemsetAsync(ldpc_errors, 0, sizeof(int32_t) * nK, stream));
+            if (crc_extracted) FT8B_CUDA_TRY(cudaMemsetAsync(crc_extracted, 0, sizeof(int32_t) * nK, stream));
+            if (crc_calculated) FT8B_CUDA_TRY(cudaMemsetAsync(crc_calculated, 0, sizeof(int32_t) * nK, stream));
+            FT8B_CUDA_TRY(cudaMemsetAsync(payload, 0, 10 * nK, stream));
         }
         return 0;
     }
@@ -339,8 +366,11 @@ int ft8b_decode_slots(const void *wave, int wave_dtype, int64_t n_slots, int64_t
         {
             StageScope t(2, stream);
             const bool strict = (p->flags & FT8B_FLAG_STRICT_TOPK) != 0;       // opt-in extension, see ft8b_select_topk
+            // the spectrogram goes along: scores that decide or are returned are re-evaluated in the reference's own
+            // summation order (select_candidates_kernel, ref_sync_score)
             rc = select_candidates(scores, nb, g.nt, g.nf, g.t0, K, p->min_score, cand_time + s0 * K, cand_freq + s0 * K,
-                                   cand_score + s0 * K, n_cand + s0, nullptr, strict ? nullptr : tiles, strict ? -1 : cp.n_tiles, stream);
+                                   cand_score + s0 * K, n_cand + s0, nullptr, strict ? nullptr : tiles, strict ? -1 : cp.n_tiles,
+                                   strict ? nullptr : mag, (int)g.T, g.F, p->steps_per_symbol, p->bins_per_tone, stream);
         }
         if (rc) return rc;
         {

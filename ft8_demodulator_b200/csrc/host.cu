@@ -7,7 +7,10 @@
 // pinned torch tensor) is copied from directly; pageable memory (NumPy) is first gathered into two pinned staging
 // buffers by a few host threads, which overlaps as well because every device call here is asynchronous.
 // All device state is cached per device and reused by later calls (grow-only); ft8b_release() frees it.
+#if defined(__x86_64__) || defined(_M_X64)
 #include <emmintrin.h>
+#define FT8B_HAVE_SSE2 1
+#endif
 #include <unistd.h>
 
 #include <algorithm>
@@ -44,8 +47,12 @@ struct HostPath {
 };
 
 constexpr int kMaxDevices = 64;
-double g_last_host_ms = 0.0;                      // ft8b_last_host_call_ms
-std::mutex g_host_mu;                             // host-buffer calls are serialised (they share the cached buffers)
+thread_local double g_last_host_ms = 0.0;         // ft8b_last_host_call_ms: the calling thread's most recent call
+// One lock per device: calls that target the same device share its cached buffers and are serialised; calls on
+// different devices (one host thread per GPU) run side by side.  The staging thread pool is shared by all devices and
+// has its own lock (g_pool_mu), held only while a piece is being gathered.
+std::mutex g_dev_mu[kMaxDevices];
+std::mutex g_pool_mu;
 HostPath g_host[kMaxDevices];
 
 int grow(void **ptr, size_t *have, size_t need, bool pinned) {
@@ -95,6 +102,9 @@ void free_path(HostPath &h) {
 // Copy for the staging path: 16-byte non-temporal stores (the pinned destination is read next by the DMA engine, not by
 // a core, so it should not be pulled into the caches first: a cached store costs a read-for-ownership on top).
 void copy_stream(char *dst, const char *src, size_t n) {
+#ifndef FT8B_HAVE_SSE2
+    std::memcpy(dst, src, n);      // hosts without SSE2 (aarch64, e.g. Grace): the C library's copy
+#else
     const size_t head = std::min(n, (size_t)((16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15));
     std::memcpy(dst, src, head);
     dst += head; src += head; n -= head;
@@ -111,6 +121,7 @@ void copy_stream(char *dst, const char *src, size_t n) {
     }
     _mm_sfence();
     std::memcpy(dst + i, src + i, n - i);
+#endif
 }
 
 int env_int(const char *name, int dflt) {
@@ -237,9 +248,10 @@ private:
     pid_t pid_ = 0;
 };
 
-StagePool g_stage_pool;        // used under g_host_mu only
+StagePool g_stage_pool;        // used under g_pool_mu only
 
 void gather_rows(char *dst, const char *src, int64_t rows, size_t row_bytes, size_t src_pitch) {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
     g_stage_pool.gather(dst, src, rows, row_bytes, src_pitch);
 }
 
@@ -248,10 +260,10 @@ size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 }  // namespace
 
 int release_host_paths() {
-    std::lock_guard<std::mutex> lk(g_host_mu);
     int cur = 0;
     const bool have_cur = cudaGetDevice(&cur) == cudaSuccess;
     for (int d = 0; d < kMaxDevices; ++d) {
+        std::lock_guard<std::mutex> lk(g_dev_mu[d]);
         if (!g_host[d].live) continue;
         cudaSetDevice(d);
         free_path(g_host[d]);
@@ -265,13 +277,126 @@ int release_host_paths() {
 
 using namespace ft8b;
 
+namespace {
+
+struct HostCall {
+    const void *wave;
+    int wave_dtype;
+    int64_t n_slots, n_samples, slot_stride;
+    const ft8b_decode_params *p;
+    int64_t piece_slots;
+    void *dst[9];      // cand_time, cand_freq, cand_score, n_cand, ok, ldpc_errors, crc_extracted, crc_calculated, payload
+    bool pinned;
+};
+
+// The body of one host-memory call on an initialised HostPath.  May return at any point with work still queued on
+// h.copy / h.compute: the caller (ft8b_decode_slots_host) is the single exit path that drains both streams before
+// the cached buffers can be touched again.
+int host_call(HostPath &h, const HostCall &c) {
+    const ft8b_decode_params *p = c.p;
+    const int64_t n_slots = c.n_slots, K = p->max_candidates;
+    const size_t elt = c.wave_dtype == FT8B_DTYPE_F32 ? 4 : (c.wave_dtype == FT8B_DTYPE_I16 ? 2 : 8);
+    const size_t row_bytes = (size_t)c.n_samples * elt, src_pitch = (size_t)c.slot_stride * elt;
+    const int64_t piece = std::min<int64_t>(n_slots, c.piece_slots > 0 ? c.piece_slots : 128);
+    // ft8b_decode_workspace_bytes(piece) covers every batch of at most `piece` slots, i.e. the shorter tail piece too
+    // (whose single chunk may be larger than the balanced chunks of a full piece)
+    const int64_t work_need = ft8b_decode_workspace_bytes(p, piece, c.n_samples);
+    if (work_need < 0) return (int)work_need;     // geometry error, message already set
+    int rc = 0;
+    const int n_buf = n_slots > piece ? 2 : 1;
+    const size_t piece_bytes = std::max<size_t>((size_t)piece * row_bytes, 16);
+    if (h.audio_bytes < piece_bytes) {
+        for (int k = 0; k < 2; ++k) {
+            size_t have = h.audio[k] ? h.audio_bytes : 0;
+            if ((rc = grow(&h.audio[k], &have, piece_bytes, false))) { h.audio_bytes = 0; return rc; }
+        }
+        h.audio_bytes = piece_bytes;
+    }
+    if (!c.pinned && h.stage_bytes < piece_bytes) {
+        for (int k = 0; k < 2; ++k) {
+            size_t have = h.stage[k] ? h.stage_bytes : 0;
+            if ((rc = grow(&h.stage[k], &have, piece_bytes, true))) { h.stage_bytes = 0; return rc; }
+        }
+        h.stage_bytes = piece_bytes;
+    }
+    if ((rc = grow(&h.work, &h.work_bytes, (size_t)work_need, false))) return rc;
+    // device result arrays [n_slots][K]
+    const size_t nK = (size_t)n_slots * (size_t)K;
+    size_t off[10];
+    off[0] = 0;                                        // cand_time
+    off[1] = off[0] + align256(4 * nK);                // cand_freq
+    off[2] = off[1] + align256(4 * nK);                // cand_score
+    off[3] = off[2] + align256(8 * nK);                // n_cand
+    off[4] = off[3] + align256(4 * (size_t)n_slots);   // ok
+    off[5] = off[4] + align256(nK);                    // ldpc_errors
+    off[6] = off[5] + align256(4 * nK);                // crc_extracted
+    off[7] = off[6] + align256(4 * nK);                // crc_calculated
+    off[8] = off[7] + align256(4 * nK);                // payload
+    off[9] = off[8] + align256(10 * nK);
+    {
+        void *r = h.res;
+        rc = grow(&r, &h.res_bytes, std::max<size_t>(off[9], 256), false);
+        h.res = static_cast<char *>(r);
+        if (rc) return rc;
+        if ((rc = grow(&h.res_host, &h.res_host_bytes, std::max<size_t>(off[9], 256), true))) return rc;
+    }
+    FT8B_CUDA_TRY(cudaEventRecord(h.t_beg, h.compute));
+    FT8B_CUDA_TRY(cudaMemsetAsync(h.res, 0, off[9], h.compute));
+    FT8B_CUDA_TRY(cudaStreamWaitEvent(h.copy, h.t_beg, 0));      // no copy of this call starts before its time origin
+
+    bool staged[2] = {false, false};
+    int64_t i = 0;
+    for (int64_t lo = 0; lo < n_slots; lo += piece, ++i) {
+        const int64_t n = std::min(piece, n_slots - lo);
+        const int k = (int)(i % n_buf);
+        const char *src = static_cast<const char *>(c.wave) + (size_t)lo * src_pitch;
+        size_t pitch = src_pitch;
+        if (!c.pinned) {
+            // stage[k] is free once the copy that last read it has finished
+            if (staged[k]) FT8B_CUDA_TRY(cudaEventSynchronize(h.ready[k]));
+            gather_rows(static_cast<char *>(h.stage[k]), src, n, row_bytes, src_pitch);
+            src = static_cast<const char *>(h.stage[k]);
+            pitch = row_bytes;
+            staged[k] = true;
+        }
+        if (i >= n_buf) FT8B_CUDA_TRY(cudaStreamWaitEvent(h.copy, h.done[k], 0));     // audio[k] no longer read
+        if (row_bytes > 0)
+            FT8B_CUDA_TRY(cudaMemcpy2DAsync(h.audio[k], row_bytes, src, pitch, row_bytes, (size_t)n, cudaMemcpyHostToDevice, h.copy));
+        FT8B_CUDA_TRY(cudaEventRecord(h.ready[k], h.copy));
+        FT8B_CUDA_TRY(cudaStreamWaitEvent(h.compute, h.ready[k], 0));
+        rc = ft8b_decode_slots(h.audio[k], c.wave_dtype, n, c.n_samples, c.n_samples, p, h.work, (int64_t)h.work_bytes,
+                               reinterpret_cast<int32_t *>(h.res + off[0]) + lo * K, reinterpret_cast<int32_t *>(h.res + off[1]) + lo * K,
+                               reinterpret_cast<double *>(h.res + off[2]) + lo * K, reinterpret_cast<int32_t *>(h.res + off[3]) + lo,
+                               reinterpret_cast<uint8_t *>(h.res + off[4]) + lo * K, reinterpret_cast<int32_t *>(h.res + off[5]) + lo * K,
+                               reinterpret_cast<int32_t *>(h.res + off[6]) + lo * K, reinterpret_cast<int32_t *>(h.res + off[7]) + lo * K,
+                               reinterpret_cast<uint8_t *>(h.res + off[8]) + lo * K * 10, h.compute);
+        if (rc) return rc;
+        FT8B_CUDA_TRY(cudaEventRecord(h.done[k], h.compute));
+    }
+    // results: one copy of the whole result block into the pinned mirror (nine copies into pageable caller arrays would
+    // each be staged and waited for by the driver), then plain memcpy into the caller's arrays
+    FT8B_CUDA_TRY(cudaMemcpyAsync(h.res_host, h.res, off[9], cudaMemcpyDeviceToHost, h.compute));
+    FT8B_CUDA_TRY(cudaEventRecord(h.t_end, h.compute));
+    FT8B_CUDA_TRY(cudaStreamSynchronize(h.compute));
+    FT8B_CUDA_TRY(cudaStreamSynchronize(h.copy));
+    const size_t len[9] = {4 * nK, 4 * nK, 8 * nK, 4 * (size_t)n_slots, nK, 4 * nK, 4 * nK, 4 * nK, 10 * nK};
+    for (int a = 0; a < 9; ++a)
+        if (len[a] && c.dst[a]) std::memcpy(c.dst[a], static_cast<const char *>(h.res_host) + off[a], len[a]);
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h.t_beg, h.t_end) == cudaSuccess) g_last_host_ms = ms;
+    else cudaGetLastError();
+    return 0;
+}
+
+}  // namespace
+
 extern "C" int ft8b_decode_slots_host(const void *wave, int wave_dtype, int64_t n_slots, int64_t n_samples, int64_t slot_stride,
                                       const ft8b_decode_params *p, int device, int64_t piece_slots, int32_t *cand_time,
                                       int32_t *cand_freq, double *cand_score, int32_t *n_cand, uint8_t *ok,
                                       int32_t *ldpc_errors, int32_t *crc_extracted, int32_t *crc_calculated,
                                       uint8_t *payload) {
-    if (!p || (!wave && n_slots > 0) || !cand_time || !cand_freq || !cand_score || !n_cand || !ok || !ldpc_errors ||
-        !crc_extracted || !crc_calculated || !payload)
+    // crc_extracted / crc_calculated may be NULL (not wanted), as in ft8b_decode_slots; every other array is required
+    if (!p || (!wave && n_slots > 0) || !cand_time || !cand_freq || !cand_score || !n_cand || !ok || !ldpc_errors || !payload)
         FT8B_ARG_FAIL("ft8b_decode_slots_host: null pointer");
     if (wave_dtype != FT8B_DTYPE_F32 && wave_dtype != FT8B_DTYPE_F64 && wave_dtype != FT8B_DTYPE_I16)
         FT8B_ARG_FAIL("ft8b_decode_slots_host: bad dtype");
@@ -299,129 +424,45 @@ extern "C" int ft8b_decode_slots_host(const void *wave, int wave_dtype, int64_t 
     }
     if (dev < 0 || dev >= kMaxDevices) FT8B_ARG_FAIL("ft8b_decode_slots_host: device ordinal %d", dev);
 
-    const int64_t K = p->max_candidates;
-    const size_t elt = wave_dtype == FT8B_DTYPE_F32 ? 4 : (wave_dtype == FT8B_DTYPE_I16 ? 2 : 8);
-    const size_t row_bytes = (size_t)n_samples * elt, src_pitch = (size_t)slot_stride * elt;
-    const int64_t piece = std::min<int64_t>(n_slots, piece_slots > 0 ? piece_slots : 128);
-    const int64_t work_need = ft8b_decode_workspace_bytes(p, piece, n_samples);
-    if (work_need < 0) return (int)work_need;     // geometry error, message already set
-
+    HostCall c{wave, wave_dtype, n_slots, n_samples, slot_stride, p, piece_slots,
+               {cand_time, cand_freq, cand_score, n_cand, ok, ldpc_errors, crc_extracted, crc_calculated, payload}, false};
     // is the caller's buffer page-locked (then the DMA engine reads it directly)?
     cudaPointerAttributes attr;
-    bool pinned = false;
     if (cudaPointerGetAttributes(&attr, wave) == cudaSuccess) {
         if (attr.type == cudaMemoryTypeDevice) FT8B_ARG_FAIL("ft8b_decode_slots_host: wave is a device pointer (use ft8b_decode_slots)");
-        pinned = attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged;
+        c.pinned = attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged;
     } else {
         cudaGetLastError();      // an address CUDA knows nothing about: pageable
     }
 
-    std::lock_guard<std::mutex> lk(g_host_mu);
+    std::lock_guard<std::mutex> lk(g_dev_mu[dev]);
     HostPath &h = g_host[dev];
     int rc = init_path(h);
-    if (rc) return rc;
-    const int n_buf = n_slots > piece ? 2 : 1;
-    const size_t piece_bytes = std::max<size_t>((size_t)piece * row_bytes, 16);
-    if (h.audio_bytes < piece_bytes) {
-        for (int k = 0; k < 2; ++k) {
-            size_t have = h.audio[k] ? h.audio_bytes : 0;
-            if ((rc = grow(&h.audio[k], &have, piece_bytes, false))) return rc;
+    if (rc == 0) rc = host_call(h, c);
+    if (rc != 0) {
+        // Single failure exit: nothing of this call may still be queued when the cached buffers are reused.  Drain both
+        // streams; after a CUDA error (rc > 0) the streams, events and buffers are in an unknown state, so the whole
+        // cached path is dropped and the next call builds a fresh one.  The error message set by the failing step is kept.
+        if (h.copy) cudaStreamSynchronize(h.copy);
+        if (h.compute) cudaStreamSynchronize(h.compute);
+        if (rc > 0) {
+            h.live = true;       // free_path() releases whatever init_path() managed to create
+            free_path(h);
         }
-        h.audio_bytes = piece_bytes;
+        cudaGetLastError();
     }
-    if (!pinned && h.stage_bytes < piece_bytes) {
-        for (int k = 0; k < 2; ++k) {
-            size_t have = h.stage[k] ? h.stage_bytes : 0;
-            if ((rc = grow(&h.stage[k], &have, piece_bytes, true))) return rc;
-        }
-        h.stage_bytes = piece_bytes;
-    }
-    if ((rc = grow(&h.work, &h.work_bytes, (size_t)work_need, false))) return rc;
-    // device result arrays [n_slots][K]
-    const size_t nK = (size_t)n_slots * (size_t)K;
-    size_t off[10];
-    off[0] = 0;                                        // cand_time
-    off[1] = off[0] + align256(4 * nK);                // cand_freq
-    off[2] = off[1] + align256(4 * nK);                // cand_score
-    off[3] = off[2] + align256(8 * nK);                // n_cand
-    off[4] = off[3] + align256(4 * (size_t)n_slots);   // ok
-    off[5] = off[4] + align256(nK);                    // ldpc_errors
-    off[6] = off[5] + align256(4 * nK);                // crc_extracted
-    off[7] = off[6] + align256(4 * nK);                // crc_calculated
-    off[8] = off[7] + align256(4 * nK);                // payload
-    off[9] = off[8] + align256(10 * nK);
-    {
-        void *r = h.res;
-        if ((rc = grow(&r, &h.res_bytes, std::max<size_t>(off[9], 256), false))) return rc;
-        h.res = static_cast<char *>(r);
-        if ((rc = grow(&h.res_host, &h.res_host_bytes, std::max<size_t>(off[9], 256), true))) return rc;
-    }
-    FT8B_CUDA_TRY(cudaEventRecord(h.t_beg, h.compute));
-    FT8B_CUDA_TRY(cudaMemsetAsync(h.res, 0, off[9], h.compute));
-    FT8B_CUDA_TRY(cudaStreamWaitEvent(h.copy, h.t_beg, 0));      // no copy of this call starts before its time origin
-
-    bool staged[2] = {false, false};
-    int64_t i = 0;
-    for (int64_t lo = 0; lo < n_slots; lo += piece, ++i) {
-        const int64_t n = std::min(piece, n_slots - lo);
-        const int k = (int)(i % n_buf);
-        const char *src = static_cast<const char *>(wave) + (size_t)lo * src_pitch;
-        size_t pitch = src_pitch;
-        if (!pinned) {
-            // stage[k] is free once the copy that last read it has finished
-            if (staged[k]) FT8B_CUDA_TRY(cudaEventSynchronize(h.ready[k]));
-            gather_rows(static_cast<char *>(h.stage[k]), src, n, row_bytes, src_pitch);
-            src = static_cast<const char *>(h.stage[k]);
-            pitch = row_bytes;
-            staged[k] = true;
-        }
-        if (i >= n_buf) FT8B_CUDA_TRY(cudaStreamWaitEvent(h.copy, h.done[k], 0));     // audio[k] no longer read
-        if (row_bytes > 0)
-            FT8B_CUDA_TRY(cudaMemcpy2DAsync(h.audio[k], row_bytes, src, pitch, row_bytes, (size_t)n, cudaMemcpyHostToDevice, h.copy));
-        FT8B_CUDA_TRY(cudaEventRecord(h.ready[k], h.copy));
-        FT8B_CUDA_TRY(cudaStreamWaitEvent(h.compute, h.ready[k], 0));
-        rc = ft8b_decode_slots(h.audio[k], wave_dtype, n, n_samples, n_samples, p, h.work, (int64_t)h.work_bytes,
-                               reinterpret_cast<int32_t *>(h.res + off[0]) + lo * K, reinterpret_cast<int32_t *>(h.res + off[1]) + lo * K,
-                               reinterpret_cast<double *>(h.res + off[2]) + lo * K, reinterpret_cast<int32_t *>(h.res + off[3]) + lo,
-                               reinterpret_cast<uint8_t *>(h.res + off[4]) + lo * K, reinterpret_cast<int32_t *>(h.res + off[5]) + lo * K,
-                               reinterpret_cast<int32_t *>(h.res + off[6]) + lo * K, reinterpret_cast<int32_t *>(h.res + off[7]) + lo * K,
-                               reinterpret_cast<uint8_t *>(h.res + off[8]) + lo * K * 10, h.compute);
-        if (rc) {
-            cudaStreamSynchronize(h.copy);
-            cudaStreamSynchronize(h.compute);
-            return rc;
-        }
-        FT8B_CUDA_TRY(cudaEventRecord(h.done[k], h.compute));
-    }
-    // results: one copy of the whole result block into the pinned mirror (nine copies into pageable caller arrays would
-    // each be staged and waited for by the driver), then plain memcpy into the caller's arrays
-    FT8B_CUDA_TRY(cudaMemcpyAsync(h.res_host, h.res, off[9], cudaMemcpyDeviceToHost, h.compute));
-    FT8B_CUDA_TRY(cudaEventRecord(h.t_end, h.compute));
-    FT8B_CUDA_TRY(cudaStreamSynchronize(h.compute));
-    FT8B_CUDA_TRY(cudaStreamSynchronize(h.copy));
-    void *dst[9] = {cand_time, cand_freq, cand_score, n_cand, ok, ldpc_errors, crc_extracted, crc_calculated, payload};
-    const size_t len[9] = {4 * nK, 4 * nK, 8 * nK, 4 * (size_t)n_slots, nK, 4 * nK, 4 * nK, 4 * nK, 10 * nK};
-    for (int a = 0; a < 9; ++a)
-        if (len[a]) std::memcpy(dst[a], static_cast<const char *>(h.res_host) + off[a], len[a]);
-    float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, h.t_beg, h.t_end) == cudaSuccess) g_last_host_ms = ms;
-    else cudaGetLastError();
-    return 0;
+    return rc;
 }
 
 extern "C" int ft8b_set_host_staging(int threads, int non_temporal) {
-    std::lock_guard<std::mutex> lk(g_host_mu);
+    std::lock_guard<std::mutex> lk(g_pool_mu);
     return g_stage_pool.configure(threads, non_temporal != 0 ? 1 : 0);
 }
 
 extern "C" int ft8b_selftest_host_staging(void *dst, const void *src, int64_t rows, int64_t row_bytes, int64_t src_pitch) {
     if (!dst || !src || rows < 0 || row_bytes < 0 || src_pitch < row_bytes) FT8B_ARG_FAIL("ft8b_selftest_host_staging: bad argument");
-    std::lock_guard<std::mutex> lk(g_host_mu);
     gather_rows(static_cast<char *>(dst), static_cast<const char *>(src), rows, (size_t)row_bytes, (size_t)src_pitch);
     return 0;
 }
 
-extern "C" double ft8b_last_host_call_ms(void) {
-    std::lock_guard<std::mutex> lk(g_host_mu);
-    return g_last_host_ms;
-}
+extern "C" double ft8b_last_host_call_ms(void) { return g_last_host_ms; }

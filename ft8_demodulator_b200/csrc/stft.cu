@@ -332,6 +332,13 @@ static int get_plan(int nperseg, int nfft, bool cplx, const StftPlan **out) {
         long double ang = -two_pi * (long double)k / (long double)nfft;
         twp[k] = make_double2((double)cosl(ang), (double)sinl(ang));
     }
+    if (nperseg == 1920 && nfft == 3840 && !cplx) {
+        // Quarter-turn symmetry made exact in the table: W^k = -i conj(W^(960-k)), so entries 480..960 are the mirrored
+        // entries 480..0.  The specialised kernel may then keep only entries 0..480 (in shared memory) and form the rest
+        // on the fly, and still agree bit for bit with every path that reads the full table.
+        twp[480] = make_double2(0.70710678118654752440, -0.70710678118654752440);
+        for (int k = 481; k <= 960; ++k) twp[k] = make_double2(-twp[960 - k].y, -twp[960 - k].x);
+    }
     std::vector<double> win(nperseg);
     double wsum = 0.0;
     for (int i = 0; i < nperseg; ++i) {  // scipy get_window('hann', nperseg): periodic Hann
@@ -394,6 +401,14 @@ static int get_plan(int nperseg, int nfft, bool cplx, const StftPlan **out) {
     return 0;
 }
 
+#ifdef FT8B_STFT_PROF
+extern "C" int ft8b_debug_stft_prof(unsigned long long *out, int reset) {
+    if (out) cudaMemcpyFromSymbol(out, g_stft_prof, sizeof(g_stft_prof));
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_stft_prof, z, sizeof(z)); }
+    return 0;
+}
+#endif
+
 int release_plans() {
     std::lock_guard<std::mutex> lk(g_plan_mu);
     for (auto &kv : g_plans) {
@@ -434,7 +449,10 @@ int stft_db(const void *wave, int wave_dtype, int64_t n_slots, int64_t n_samples
         const int64_t items = n_slots * f.frames_out;
         // grid-stride CTAs: 3 per SM x 148 SMs x 16 waves (measured per 4096 slots: 1 wave 8.47 ms, 4: 8.12, 8: 8.02,
         // 16: 7.98, 64: 8.05 - the block scheduler evens out SMs; beyond 16 the per-CTA table staging shows)
-        constexpr int64_t kGrid1920 = 148 * 3 * 16;
+#ifndef FT8B_STFT_WAVES
+#define FT8B_STFT_WAVES 16
+#endif
+        constexpr int64_t kGrid1920 = 148 * 3 * FT8B_STFT_WAVES;
         const int64_t g1920 = items < kGrid1920 ? items : kGrid1920;
         // vector loads of sample pairs need every frame start to be 2-element aligned
         // the staged path copies sample pairs with cp.async: every frame start must be pair aligned

@@ -15,6 +15,18 @@
 
 #include "common.cuh"
 
+#ifdef FT8B_STFT_PROF
+// experiment build only (tools/build_variant.sh ... -DFT8B_STFT_PROF): warp-cycles per phase of the frame loop
+__device__ unsigned long long g_stft_prof[16];
+#define FT8B_PROF_DECL long long _pt = clock64(); unsigned long long _pa[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define FT8B_PROF(i) do { const long long _n = clock64(); _pa[i] += (unsigned long long)(_n - _pt); _pt = _n; } while (0)
+#define FT8B_PROF_END do { if ((threadIdx.x & 31) == 0) for (int _i = 0; _i < 8; ++_i) atomicAdd(&g_stft_prof[_i], _pa[_i]); } while (0)
+#else
+#define FT8B_PROF_DECL
+#define FT8B_PROF(i)
+#define FT8B_PROF_END
+#endif
+
 namespace ft8b {
 
 constexpr int kM1920 = 1920;
@@ -263,9 +275,16 @@ __device__ __forceinline__ double to_sample(float v) { return (double)v; }
 __device__ __forceinline__ double to_sample(double v) { return v; }
 __device__ __forceinline__ double to_sample(short v) { return from_pcm16(v); }
 
+#ifndef FT8B_STFT_SMEMTAB
+#define FT8B_STFT_SMEMTAB 0
+#endif
+constexpr int kTw3Cols = 121;       // columns 0..120 of tw3 are the only ones P3 touches
+constexpr int kTwpLen = 481;        // post-twiddles 0..480; 481..960 follow from W^k = -i conj(W^(960-k))
+constexpr int kSmemTabLen = FT8B_STFT_SMEMTAB ? 7 * kTw3Cols + kTwpLen : 0;
+
 template <typename WaveT, bool VEC>
 constexpr size_t stft1920_smem_bytes() {
-    return sizeof(double2) * (kM1920 + 512 + 16 * 15) + (VEC ? sizeof(WaveT) * kM1920 : 16);
+    return sizeof(double2) * (kM1920 + 512 + 16 * 15 + kSmemTabLen) + (VEC ? sizeof(WaveT) * kM1920 : 16);
 }
 
 // MB = CTAs per SM the register allocation must allow.  3 (168 registers, no spills, 12 warps/SM, 92 KB of L1 left
@@ -278,8 +297,23 @@ __global__ void __launch_bounds__(kStft1920Threads, MB) stft1920_kernel(const St
     double2 *logtab8 = s + kM1920;                                  // [64][8] interleaved copies of the log table
     double2 *tw2s = logtab8 + 512;                                // [16*15]
     // VEC path: the next frame's 1920 samples are staged here with cp.async while this frame is transformed
+#if FT8B_STFT_SMEMTAB
+    // P3 twiddles and post-twiddles live in shared memory (21 KB per CTA, 215 KB for the three CTAs of an SM): their
+    // 11 loads per thread and frame no longer depend on what the audio and spectrogram streams leave of L1
+    double2 *tw3s = tw2s + 16 * 15;                               // [7][121]  rows t = 1..7
+    double2 *twps = tw3s + 7 * kTw3Cols;                          // [481]
+    WaveT *xs = reinterpret_cast<WaveT *>(twps + kTwpLen);        // [1920]
+#else
     WaveT *xs = reinterpret_cast<WaveT *>(tw2s + 16 * 15);        // [1920]
+#endif
     const int tid = threadIdx.x;
+#if FT8B_STFT_SMEMTAB
+    for (int i = tid; i < 7 * kTw3Cols; i += kStft1920Threads) {
+        const int t = i / kTw3Cols + 1, j = i - (t - 1) * kTw3Cols;
+        tw3s[i] = __ldg(&a.tw3[t * kTw3Stride + j]);
+    }
+    for (int i = tid; i < kTwpLen; i += kStft1920Threads) twps[i] = __ldg(&a.twpost[i]);
+#endif
     for (int i = tid; i < 512; i += kStft1920Threads) logtab8[i] = __ldg(&a.logtab[i >> 3]);
     const double2 *logtab = logtab8 + (tid & 7);                  // this lane's copy
     for (int i = tid; i < 16 * 15; i += kStft1920Threads) tw2s[i] = __ldg(&a.tw2[i]);
@@ -307,12 +341,14 @@ __global__ void __launch_bounds__(kStft1920Threads, MB) stft1920_kernel(const St
     };
     stage_audio(blockIdx.x);
     __syncthreads();
+    FT8B_PROF_DECL
     for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int64_t slot = item / a.frames_out;
         const int64_t fr = item - slot * a.frames_out;
         const WaveT *x = VEC ? xs : frame_audio(item);
         double *out = a.mag + (slot * a.frames_out + fr) * (int64_t)Fout;
         if (VEC) __pipeline_wait_prior(0);     // this thread's pairs of this frame have landed
+        FT8B_PROF(0);
         // ---------------- P1: radix 15, inputs z[j + 128 t] = (w x)[2n] + i (w x)[2n+1], zero for n >= 960
         {
             double2 u[15];
@@ -332,15 +368,19 @@ __global__ void __launch_bounds__(kStft1920Threads, MB) stft1920_kernel(const St
                 }
             }
             bf15<true>(u);                     // u[8..14] (the zero padding) are outputs only
+            FT8B_PROF(1);
             // Barrier here rather than at the end of the loop: warps that finished the previous frame's P3 early
             // have already loaded and transformed their share of this frame; `s` (still read by slower warps in
             // P3) and the audio staging buffer are only touched after everybody has arrived.
             __syncthreads();
+            FT8B_PROF(2);
 #pragma unroll
             for (int pos = 0; pos < 15; ++pos) s[tid * 15 + out15(pos)] = u[pos];
         }
         stage_audio(item + gridDim.x);         // lands during P2/P3
+        FT8B_PROF(1);
         __syncthreads();
+        FT8B_PROF(2);
         // ---------------- P2: radix 16, Ns = 15
         // Butterfly j = 15 g + k runs on lane k of 16-lane group g (lane 15 of each group idles): the 8 lanes of
         // every quarter-warp then touch consecutive k, so the tw2s reads and the transposed stores below are
@@ -356,14 +396,18 @@ __global__ void __launch_bounds__(kStft1920Threads, MB) stft1920_kernel(const St
                 for (int t = 1; t < 16; ++t) u[t] = cmul(u[t], tw2s[t * 15 + k]);
                 bf16(u);
             }
+            FT8B_PROF(3);
             __syncthreads();
+            FT8B_PROF(4);
             if (k < 15) {
                 const int j0 = 240 * g + k;
 #pragma unroll
                 for (int pos = 0; pos < 16; ++pos) s[j0 + 15 * out16(pos)] = u[pos];
             }
         }
+        FT8B_PROF(3);
         __syncthreads();
+        FT8B_PROF(4);
         // ---------------- P3: radix 8, Ns = 240, paired butterflies + untangling + dB store
         // Thread i in 0..118 owns butterflies (i+1, 239-i): outputs u1[t] = Z[k], k = i+1 + 240 t, and Z[M-k] from the
         // second.  Its twiddles are W^(t (240 - j1)) = W8^t conj(W^(t j1)): the conjugates of the first butterfly's
@@ -383,12 +427,17 @@ __global__ void __launch_bounds__(kStft1920Threads, MB) stft1920_kernel(const St
             for (int t = 0; t < 8; ++t) { u1[t] = s[j1 + 240 * t]; u2[t] = s[j2 + 240 * t]; }
 #pragma unroll
             for (int t = 1; t < 8; ++t) {
+#if FT8B_STFT_SMEMTAB
+                const double2 w = tw3s[(t - 1) * kTw3Cols + j1];
+#else
                 const double2 w = __ldg(&a.tw3[t * kTw3Stride + j1]);
+#endif
                 u1[t] = cmul(u1[t], w);
                 u2[t] = cmul(u2[t], make_double2(w.x, -w.y));
             }
             bf8(u1);
             bf8(u2);
+            FT8B_PROF(5);
             if (full) {
                 // bins 0..1919 are all stored: k = j1 + 240 t ascending from p1, M-k descending from p2,
                 // every address an immediate offset from three per-thread base pointers
@@ -402,7 +451,19 @@ __global__ void __launch_bounds__(kStft1920Threads, MB) stft1920_kernel(const St
 #pragma unroll
                 for (int h = 0; h < 4; ++h) {
                     // W3840^(k + 960) = -i W3840^k: bins k = j1 + 240 h and k + 960 share one post-twiddle load
+#if FT8B_STFT_SMEMTAB
+                    // k = j1 + 240 h; beyond 480 the table is mirrored: W^k = -i conj(W^(960-k)) = (-y, -x) of entry 960-k
+                    // (get_plan builds entries 480..960 of the global table by this very rule, so both forms agree bit for bit)
+                    double2 w;
+                    if (h < 2) {
+                        w = twps[j1 + 240 * h];
+                    } else {
+                        const double2 m = twps[960 - 240 * h - j1];
+                        w = make_double2(-m.y, -m.x);
+                    }
+#else
                     const double2 w = __ldg(twp + 240 * h);
+#endif
 #pragma unroll
                     for (int q = 0; q < 2; ++q) {
                         const int t = h + 4 * q;
@@ -417,7 +478,9 @@ __global__ void __launch_bounds__(kStft1920Threads, MB) stft1920_kernel(const St
                 for (int t = 0; t < 8; ++t) emit_pair(u1[t], u2[(8 - t) & 7], j1 + 240 * t, mirror || (t == 0 && nyquist), a, out, logtab);
             }
         }
+        FT8B_PROF(6);
     }
+    FT8B_PROF_END;
 }
 
 }  // namespace ft8b

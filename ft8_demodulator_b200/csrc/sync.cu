@@ -254,7 +254,8 @@ namespace ft8b {
 // ------------------------------------------------------------------------------------------
 // S2b: selection.  One CTA per slot scans the score map in scan order (flat index = scan order).
 // ------------------------------------------------------------------------------------------
-constexpr int kSelThreads = 1024;
+constexpr int kSelThreads = 1024;            // select_topk_kernel; select_candidates_kernel takes its own count
+constexpr int kSelWarps = kSelThreads / 32;
 constexpr int kSelPerThread = 4;   // consecutive scores per thread per chunk
 
 struct SelArgs {
@@ -266,7 +267,94 @@ struct SelArgs {
     double *cand_score;
     const SyncTile *tiles;  // [n_slots][n_tiles] strip arg-maxima from the sync kernel, or null: phase B scans the map
     int n_tiles;
+    // Spectrogram the score map was made from, or null.  With it every score a DECISION or a RESULT hangs on is
+    // re-evaluated as the reference's own running sum (ref_sync_score below): the returned cand_score, the order of the
+    // list, threshold tests of scores within kSelTol of min_score, and the record replacement.
+    const double *mag;      // [n_slots][T][F]
+    int T, F, s, b, nb;
 };
+
+// The sync kernels add per cell, then per Costas block, then per score (what lets neighbouring candidates share work);
+// the reference keeps ONE running sum.  The two agree to ~1e-13 relative, not bit for bit.
+constexpr double kSelTol = 1e-9;
+
+// ft8_sync_score exactly as the reference evaluates it (ft8_decode.py:47-100): one running `score +=` over the Costas
+// cells in (m, k) order, each cell adding p - lower tone, p - higher tone, p - earlier symbol, p - later symbol in that
+// order, then ONE IEEE division by the comparison count.  Same bits as NumPy float64 on the same spectrogram.
+__device__ double ref_sync_score(const double *mag, int F, int s, int b, int nb, int at, int af) {
+    int base = at / s;                                     // Python floor division (:58)
+    if ((at % s) != 0 && at < 0) --base;
+    double score = 0.0;
+    int n = 0;
+    for (int m = 0; m < kNumSync; ++m) {
+#pragma unroll
+        for (int k = 0; k < kLenSync; ++k) {
+            const int block = m * kSyncOffset + k;
+            const int ba = base + block;
+            if (ba < 0 || ba >= nb) continue;              // :68-69
+            const int tone = kCostas[k];
+            const double *cell = mag + (int64_t)(at + block * s) * F + af + tone * b;
+            const double p = __ldg(cell);
+            if (tone > 0) { score = __dadd_rn(score, __dsub_rn(p, __ldg(cell - b))); ++n; }                     // :76-78
+            if (tone < 7) { score = __dadd_rn(score, __dsub_rn(p, __ldg(cell + b))); ++n; }                     // :80-82
+            if (k > 0 && ba > 0) { score = __dadd_rn(score, __dsub_rn(p, __ldg(cell - (int64_t)s * F))); ++n; }           // :85-87
+            if (k < kLenSync - 1 && ba + 1 < nb) { score = __dadd_rn(score, __dsub_rn(p, __ldg(cell + (int64_t)s * F))); ++n; }   // :89-91
+        }
+    }
+    if (n == 0 || isnan(score) || isinf(score)) return -INFINITY;       // :94-95
+    return __ddiv_rn(score, (double)n);
+}
+
+// The same value computed by a whole warp: the up to 105 spectrogram values of the score (21 Costas cells x {p, lower,
+// higher, earlier, later}) are fetched in parallel, four per lane, then every lane forms the running sum in the
+// reference's order from its neighbours' registers - the loads of one score overlap instead of following each other
+// down a chain of 84 dependent additions (one thread per score: 1.2 ms per 4096 slots; this: see DESIGN.md).
+__device__ double ref_sync_score_warp(const double *mag, int F, int s, int b, int nb, int at, int af, int lane) {
+    constexpr int kC[7] = {3, 1, 4, 0, 6, 5, 2};
+    int base = at / s;
+    if ((at % s) != 0 && at < 0) --base;
+    double r[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int v = lane + 32 * q;                       // value index = 5 * cell + j
+        double x = 0.0;
+        if (v < 105) {
+            const int cell = v / 5, j = v - 5 * cell;
+            const int m = cell / 7, k = cell - 7 * m;
+            const int block = m * kSyncOffset + k, ba = base + block;
+            const int tone = kCostas[k];
+            bool ok = ba >= 0 && ba < nb;
+            int64_t col = at + block * s;
+            int bin = af + tone * b;
+            if (j == 1) { ok = ok && tone > 0; bin -= b; }
+            else if (j == 2) { bin += b; }
+            else if (j == 3) { ok = ok && k > 0 && ba > 0; col -= s; }
+            else if (j == 4) { ok = ok && k < kLenSync - 1 && ba + 1 < nb; col += s; }
+            if (ok) x = __ldg(mag + col * F + bin);
+        }
+        r[q] = x;
+    }
+    double score = 0.0;
+    int n = 0;
+#pragma unroll
+    for (int cell = 0; cell < 21; ++cell) {
+        const int m = cell / 7, k = cell % 7;
+        const int ba = base + m * kSyncOffset + k;
+        // every lane evaluates every shuffle (no divergence around them); the terms are only added where the reference adds
+        const double p = __shfl_sync(0xffffffffu, r[(5 * cell) >> 5], (5 * cell) & 31);
+        const double lo = __shfl_sync(0xffffffffu, r[(5 * cell + 1) >> 5], (5 * cell + 1) & 31);
+        const double hi = __shfl_sync(0xffffffffu, r[(5 * cell + 2) >> 5], (5 * cell + 2) & 31);
+        const double ea = __shfl_sync(0xffffffffu, r[(5 * cell + 3) >> 5], (5 * cell + 3) & 31);
+        const double la = __shfl_sync(0xffffffffu, r[(5 * cell + 4) >> 5], (5 * cell + 4) & 31);
+        if (ba < 0 || ba >= nb) continue;
+        if (kC[k] > 0) { score = __dadd_rn(score, __dsub_rn(p, lo)); ++n; }
+        { score = __dadd_rn(score, __dsub_rn(p, hi)); ++n; }
+        if (k > 0 && ba > 0) { score = __dadd_rn(score, __dsub_rn(p, ea)); ++n; }
+        if (k < kLenSync - 1 && ba + 1 < nb) { score = __dadd_rn(score, __dsub_rn(p, la)); ++n; }
+    }
+    if (n == 0 || isnan(score) || isinf(score)) return -INFINITY;
+    return __ddiv_rn(score, (double)n);
+}
 
 __device__ __forceinline__ bool sel_pass(double v, double thr) {
     // ft8_decode.py:127: skip if score == -inf or score < min_score
@@ -277,7 +365,12 @@ __device__ __forceinline__ bool sel_better(double sa, long long ia, double sb, l
     return (sa > sb) || (sa == sb && ia < ib);
 }
 
-__global__ void __launch_bounds__(kSelThreads) select_candidates_kernel(const SelArgs a) {
+// THREADS: 256 for short lists (K <= 64: four CTAs per SM hide each other's barrier and DRAM latencies - 0.235 ms per
+// 4096 slots at K = 20 against 0.47 ms with one 1024-thread CTA per SM), 1024 for long ones (the sort and the
+// compaction of thousands of candidates want the threads).
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) select_candidates_kernel(const SelArgs a) {
+    constexpr int kSelThreads = THREADS, kSelWarps = THREADS / 32;
     extern __shared__ unsigned char sel_smem[];
     double *hs = reinterpret_cast<double *>(sel_smem);                   // [Kpad] scores
     long long *hi = reinterpret_cast<long long *>(hs + a.Kpad);          // [Kpad] scan indices
@@ -287,9 +380,12 @@ __global__ void __launch_bounds__(kSelThreads) select_candidates_kernel(const Se
     __shared__ double red_s[32];
     __shared__ long long red_i[32];
     __shared__ long long red_c[32];
+    __shared__ double s_rec_s;          // the later record (phase B): score and scan index
+    __shared__ long long s_rec_i;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int64_t slot = blockIdx.x;
     const double *sc = a.scores + slot * a.L;
+    const double *mag = a.mag ? a.mag + slot * (int64_t)a.T * a.F : nullptr;
     const int K = a.K;
 
     for (int i = tid; i < a.Kpad; i += kSelThreads) { hs[i] = -INFINITY; hi[i] = 0x7fffffffffffffffLL; }
@@ -307,6 +403,9 @@ __global__ void __launch_bounds__(kSelThreads) select_candidates_kernel(const Se
 #pragma unroll
         for (int j = 0; j < kSelPerThread; ++j) {
             v[j] = (i0 + j < a.L) ? __ldg(sc + i0 + j) : -INFINITY;
+            // a score this close to the threshold is decided on the reference's own sum (rare: ~1e-9 of all scores)
+            if (mag && fabs(v[j] - a.min_score) <= kSelTol * (1.0 + fabs(a.min_score)))
+                v[j] = ref_sync_score(mag, a.F, a.s, a.b, a.nb, a.t0 + (int)((i0 + j) / a.nf), (int)((i0 + j) % a.nf));
             cnt += sel_pass(v[j], a.min_score) ? 1 : 0;
         }
         // exclusive prefix of cnt over the block (thread order = scan order)
@@ -319,7 +418,7 @@ __global__ void __launch_bounds__(kSelThreads) select_candidates_kernel(const Se
         if (lane == 31) warp_cnt[wid] = incl;
         __syncthreads();
         if (wid == 0) {
-            int w = warp_cnt[lane];
+            int w = (lane < kSelWarps) ? warp_cnt[lane] : 0;
             int wi = w;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
@@ -349,10 +448,11 @@ __global__ void __launch_bounds__(kSelThreads) select_candidates_kernel(const Se
     }
     const int n_first = (s_base < K) ? s_base : K;
     const long long cut = s_cut;    // scan index of the K-th passer, -1 if fewer than K passers
-
     // ---- phase B: running-record replacement over the passers after the K-th ----
+    // B1: the later record = first occurrence of the maximum over the passers beyond the cut -> (s_rec_s, s_rec_i)
     long long n_pass_total = total_pass;
-    if (cut >= 0 && K > 0 && a.tiles) {
+    const bool have_later = cut >= 0 && K > 0;
+    if (have_later && a.tiles) {
         // The later record is the first occurrence of the map's maximum whenever that lies beyond the cut; if it lies
         // before the cut it is already in H as its best element and nothing later is strictly greater.  So the
         // maximum over the strip summaries decides, and the rest of the map is not read (n_pass is not available).
@@ -373,28 +473,29 @@ __global__ void __launch_bounds__(kSelThreads) select_candidates_kernel(const Se
         if (lane == 0) { red_s[wid] = bs; red_i[wid] = bi; }
         __syncthreads();
         if (wid == 0) {
-            bs = red_s[lane]; bi = red_i[lane];
+            bs = (lane < kSelWarps) ? red_s[lane] : -INFINITY;
+            bi = (lane < kSelWarps) ? red_i[lane] : 0x7fffffffffffffffLL;
 #pragma unroll
             for (int d = 16; d >= 1; d >>= 1) {
                 const double os = __shfl_xor_sync(0xffffffffu, bs, d);
                 const long long oi = __shfl_xor_sync(0xffffffffu, bi, d);
                 if (sel_better(os, oi, bs, bi)) { bs = os; bi = oi; }
             }
-            if (lane == 0 && bi > cut && sel_pass(bs, a.min_score)) {
-                int best = 0;
-                for (int i = 1; i < n_first; ++i)
-                    if (sel_better(hs[i], hi[i], hs[best], hi[best])) best = i;
-                if (bs > hs[best]) { hs[best] = bs; hi[best] = bi; }
+            if (lane == 0) {
+                const bool live = bi > cut && bi != 0x7fffffffffffffffLL;
+                s_rec_s = live ? bs : -INFINITY;
+                s_rec_i = live ? bi : 0x7fffffffffffffffLL;
             }
         }
-        __syncthreads();
         n_pass_total = -1;
-    } else if (cut >= 0 && K > 0) {
+    } else if (have_later) {
         double bs = -INFINITY;
         long long bi = 0x7fffffffffffffffLL;
         long long extra = 0;
         for (int64_t i = cut + 1 + tid; i < a.L; i += kSelThreads) {
-            const double v = __ldg(sc + i);
+            double v = __ldg(sc + i);
+            if (mag && fabs(v - a.min_score) <= kSelTol * (1.0 + fabs(a.min_score)))
+                v = ref_sync_score(mag, a.F, a.s, a.b, a.nb, a.t0 + (int)(i / a.nf), (int)(i % a.nf));
             if (sel_pass(v, a.min_score)) {
                 ++extra;
                 if (sel_better(v, i, bs, bi)) { bs = v; bi = i; }
@@ -411,7 +512,9 @@ __global__ void __launch_bounds__(kSelThreads) select_candidates_kernel(const Se
         if (lane == 0) { red_s[wid] = bs; red_i[wid] = bi; red_c[wid] = extra; }
         __syncthreads();
         if (wid == 0) {
-            bs = red_s[lane]; bi = red_i[lane]; extra = red_c[lane];
+            bs = (lane < kSelWarps) ? red_s[lane] : -INFINITY;
+            bi = (lane < kSelWarps) ? red_i[lane] : 0x7fffffffffffffffLL;
+            extra = (lane < kSelWarps) ? red_c[lane] : 0;
 #pragma unroll
             for (int d = 16; d >= 1; d >>= 1) {
                 const double os = __shfl_xor_sync(0xffffffffu, bs, d);
@@ -419,19 +522,38 @@ __global__ void __launch_bounds__(kSelThreads) select_candidates_kernel(const Se
                 extra += __shfl_xor_sync(0xffffffffu, extra, d);
                 if (sel_better(os, oi, bs, bi)) { bs = os; bi = oi; }
             }
-            if (lane == 0) {
-                // b = best of H (heap root); replace when the later record is strictly greater (:136-137)
-                int best = 0;
-                for (int i = 1; i < n_first; ++i)
-                    if (sel_better(hs[i], hi[i], hs[best], hi[best])) best = i;
-                if (bs > hs[best]) { hs[best] = bs; hi[best] = bi; }
-                red_c[0] = extra;
-            }
+            if (lane == 0) { s_rec_s = bs; s_rec_i = bi; red_c[0] = extra; }
         }
         __syncthreads();
         // passers counted so far: everything up to and including the cut chunk is not fully counted;
         // recompute as K-th passer rank (K) + later passers.
         n_pass_total = (long long)K + red_c[0];
+    } else if (tid == 0) {
+        s_rec_s = -INFINITY;
+        s_rec_i = 0x7fffffffffffffffLL;
+    }
+    __syncthreads();
+    // B2: with the spectrogram at hand, the scores of the list and of the later record as the reference computes them
+    // (what is returned, what the replacement compares and what the final sort orders by): one warp per score, the
+    // 105 spectrogram values of a score loaded in parallel, the running sum then formed in the reference's order.
+    if (mag) {
+        const long long rec_i = s_rec_i;
+        const int n_items = n_first + (rec_i != 0x7fffffffffffffffLL ? 1 : 0);
+        for (int it = wid; it < n_items; it += kSelWarps) {
+            const long long idx = (it < n_first) ? hi[it] : rec_i;
+            const double e = ref_sync_score_warp(mag, a.F, a.s, a.b, a.nb, a.t0 + (int)(idx / a.nf), (int)(idx % a.nf), lane);
+            if (lane == 0) {
+                if (it < n_first) hs[it] = e; else s_rec_s = e;
+            }
+        }
+        __syncthreads();
+    }
+    // B3: b = best of H (heap root); replaced when the later record is strictly greater (:136-137)
+    if (tid == 0 && have_later && s_rec_i != 0x7fffffffffffffffLL && sel_pass(s_rec_s, a.min_score)) {
+        int best = 0;
+        for (int i = 1; i < n_first; ++i)
+            if (sel_better(hs[i], hi[i], hs[best], hi[best])) best = i;
+        if (s_rec_s > hs[best]) { hs[best] = s_rec_s; hi[best] = s_rec_i; }
     }
     __syncthreads();
 
@@ -551,7 +673,7 @@ __global__ void __launch_bounds__(kSelThreads) select_topk_kernel(const SelArgs 
         if (lane == 31) warp_cnt[wid] = incl;
         __syncthreads();
         if (wid == 0) {
-            const int w = warp_cnt[lane];
+            const int w = (lane < kSelWarps) ? warp_cnt[lane] : 0;
             int wi = w;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
@@ -684,7 +806,8 @@ int sync_scores(const double *mag, int64_t n_slots, int T, int F, int s, int b, 
 
 int select_candidates(const double *scores, int64_t n_slots, int nt, int nf, int t0, int K, double min_score,
                       int32_t *cand_time, int32_t *cand_freq, double *cand_score, int32_t *n_cand, int32_t *n_pass,
-                      const SyncTile *tiles, int n_tiles, cudaStream_t stream) {
+                      const SyncTile *tiles, int n_tiles, const double *mag, int T, int F, int s, int b,
+                      cudaStream_t stream) {
     if (tiles && n_pass) FT8B_ARG_FAIL("select_candidates: n_pass needs the full scan (no strip summaries)");
     if (!cand_time || !cand_freq || !cand_score || !n_cand) FT8B_ARG_FAIL("ft8b_select_candidates: null pointer");
     if (K < 0 || K > FT8B_MAX_CANDIDATES) {
@@ -706,6 +829,12 @@ int select_candidates(const double *scores, int64_t n_slots, int nt, int nf, int
     a.min_score = min_score;
     a.cand_time = cand_time; a.cand_freq = cand_freq; a.cand_score = cand_score; a.n_cand = n_cand; a.n_pass = n_pass;
     a.tiles = tiles; a.n_tiles = n_tiles;
+    a.mag = mag; a.T = T; a.F = F; a.s = s; a.b = b; a.nb = (mag && s > 0) ? T / s : 0;
+    if (mag) {
+        int t0c, ntc, nfc;
+        ft8b_search_ranges(T, F, s, b, &t0c, &ntc, &nfc);
+        if (t0c != t0 || ntc != nt || nfc != nf) FT8B_ARG_FAIL("select_candidates: score map does not belong to this spectrogram geometry");
+    }
     const size_t smem = (size_t)kp * (sizeof(double) + sizeof(long long));
     if (n_tiles < 0) {       // strict top-K (opt-in extension)
         a.tiles = nullptr; a.n_tiles = 0;
@@ -714,8 +843,12 @@ int select_candidates(const double *scores, int64_t n_slots, int nt, int nf, int
         FT8B_LAUNCH_CHECK("select_topk_kernel");
         return 0;
     }
-    FT8B_CUDA_TRY(cudaFuncSetAttribute(select_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem > 48 * 1024 ? (int)smem : 48 * 1024));
-    select_candidates_kernel<<<(unsigned)n_slots, kSelThreads, smem, stream>>>(a);
+    if (K <= 64) {
+        select_candidates_kernel<256><<<(unsigned)n_slots, 256, smem, stream>>>(a);
+    } else {
+        FT8B_CUDA_TRY(cudaFuncSetAttribute(select_candidates_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem > 48 * 1024 ? (int)smem : 48 * 1024));
+        select_candidates_kernel<1024><<<(unsigned)n_slots, 1024, smem, stream>>>(a);
+    }
     FT8B_LAUNCH_CHECK("select_candidates_kernel");
     return 0;
 }

@@ -79,10 +79,12 @@ def sync_scores(mag: torch.Tensor, time_osr: int, freq_osr: int):
     return scores, t0
 
 
-def select_candidates(scores: torch.Tensor, t0: int, K: int, min_score: float, strict_topk: bool = False):
+def select_candidates(scores: torch.Tensor, t0: int, K: int, min_score: float, strict_topk: bool = False,
+                      mag: torch.Tensor = None, time_osr: int = 0, freq_osr: int = 0):
     """S2b.  scores [B, nt, nf] -> (cand_time i32 [B,K], cand_freq i32 [B,K], cand_score f64 [B,K], n_cand i32 [B],
     n_pass i32 [B]).  strict_topk (opt-in extension): the K best passers instead of the reference's list; n_pass is
-    not counted then (zeros)."""
+    not counted then (zeros).  With `mag` [B, T, F] (the spectrogram the map was made from, plus its oversampling) the
+    scores that decide or are returned are re-evaluated in the reference's own summation order (ft8b_find_candidates)."""
     assert scores.is_cuda and scores.dtype == _F64 and scores.is_contiguous() and scores.dim() == 3
     B, nt, nf = scores.shape
     dev = scores.device
@@ -94,6 +96,11 @@ def select_candidates(scores: torch.Tensor, t0: int, K: int, min_score: float, s
     if strict_topk:
         _lib.check(_lib.lib().ft8b_select_topk(_p(scores) if scores.numel() else 0, B, nt, nf, t0, K, float(min_score),
                                                _p(ct), _p(cf), _p(cs), _p(nc), _stream()), "ft8b_select_topk")
+    elif mag is not None and scores.numel():
+        assert mag.is_cuda and mag.dtype == _F64 and mag.is_contiguous() and mag.dim() == 3 and mag.shape[0] == B
+        _lib.check(_lib.lib().ft8b_find_candidates(_p(mag), _p(scores), B, mag.shape[1], mag.shape[2], time_osr, freq_osr, K,
+                                                   float(min_score), _p(ct), _p(cf), _p(cs), _p(nc), _p(npass), _stream()),
+                   "ft8b_find_candidates")
     else:
         _lib.check(_lib.lib().ft8b_select_candidates(_p(scores) if scores.numel() else 0, B, nt, nf, t0, K, float(min_score),
                                                      _p(ct), _p(cf), _p(cs), _p(nc), _p(npass), _stream()),

@@ -85,7 +85,8 @@ def ft8_find_candidates(wf: FT8Waterfall, num_candidates: int, min_score: int, s
     strict_topk=True (opt-in extension): the num_candidates best scores instead of the reference's
     "first K passers in scan order + one record replacement" list."""
     scores, t0, _ = _score_map(wf)
-    ct, cf, cs, nc, _ = engine.select_candidates(scores, t0, int(num_candidates), float(min_score), strict_topk=strict_topk)
+    ct, cf, cs, nc, _ = engine.select_candidates(scores, t0, int(num_candidates), float(min_score), strict_topk=strict_topk,
+                                                 mag=_device_waterfall(wf), time_osr=wf.time_osr, freq_osr=wf.freq_osr)
     n = int(nc.cpu()[0])
     ct, cf, cs = ct[0, :n].cpu().numpy(), cf[0, :n].cpu().numpy(), cs[0, :n].cpu().numpy()
     return [FT8Candidate(waterfall=wf, abs_time=int(ct[i]), abs_freq=int(cf[i]), score=float(cs[i])) for i in range(n)]

@@ -102,6 +102,20 @@ int ft8b_select_candidates(const double *scores, int64_t n_slots, int nt, int nf
                            int32_t *cand_time, int32_t *cand_freq, double *cand_score, int32_t *n_cand,
                            int32_t *n_pass, void *stream);
 /*
+ * ft8_find_candidates (ft8_decode.py:102-149) on a score map made by ft8b_sync_scores from `mag` (same T, F, osr): the
+ * selection above, with the spectrogram at hand.  The sync kernels add per cell, per Costas block, per score - the same
+ * terms as the reference's single running sum in a different association, equal to ~1e-13 relative but not bit for
+ * bit.  Here every score a decision or a result hangs on is re-evaluated exactly as ft8_sync_score does it
+ * (ft8_decode.py:57-100: one running sum in (m, k, lower/higher/earlier/later) order, one IEEE division): the returned
+ * cand_score, the order of the list, the threshold test of any score within 1e-9 (relative to 1 + |min_score|) of
+ * min_score, and the record replacement.  For the same spectrogram the list, its order and its scores then equal the
+ * reference's bit for bit, unless two DIFFERENT map cells compete for the map's maximum within 1e-13.
+ * ft8b_decode_slots selects this way.
+ */
+int ft8b_find_candidates(const double *mag, const double *scores, int64_t n_slots, int T, int F, int time_osr, int freq_osr,
+                         int K, double min_score, int32_t *cand_time, int32_t *cand_freq, double *cand_score,
+                         int32_t *n_cand, int32_t *n_pass, void *stream);
+/*
  * OPT-IN EXTENSION (not the reference's behaviour; SURVEY Appendix D "may add an opt-in strict top-K"): the K best
  * threshold passers by (score descending, scan position ascending), in that order - what a reader of
  * ft8_find_candidates would expect it to return.  Same outputs as ft8b_select_candidates.  In the pipeline it is
@@ -200,8 +214,12 @@ int ft8b_decode_candidates_drift(const double *mag, int64_t n_slots, int T, int 
  * Whole path, decode_ft8_message (ft8_decode.py:288-394) for a batch of equal-length slots:
  * S1 -> S2a -> S2b -> LLR in chunks of `chunk_slots` slots (the float64 spectrogram and score map exist for one
  * chunk at a time: 4.2 MB per slot at 12 kHz, osr 2x2), then one LDPC/CRC launch over the candidates of the whole
- * batch.  `workspace` must hold ft8b_decode_workspace_bytes() bytes.
- * Outputs as in ft8b_select_candidates / ft8b_decode_candidates ([n_slots][K]...).
+ * batch.  `workspace` must hold ft8b_decode_workspace_bytes(p, n_slots, n_samples) bytes; that size is an upper bound
+ * for every batch of AT MOST n_slots slots decoded with the same parameters (a workspace sized once for the largest
+ * batch serves all shorter ones, e.g. a ragged last piece).
+ * Outputs as in ft8b_select_candidates / ft8b_decode_candidates ([n_slots][K]...); every output array is fully
+ * defined on return (unused candidate positions and "nothing to search" batches hold zeros).  crc_extracted and
+ * crc_calculated may be NULL when not wanted (both entry points); every other pointer is required.
  */
 typedef struct {
     double sample_rate;
@@ -230,14 +248,17 @@ int ft8b_decode_slots(const void *wave, int wave_dtype, int64_t n_slots, int64_t
  * copied from directly; pageable memory is gathered into pinned staging buffers by persistent host threads first
  * (streaming stores; ft8b_set_host_staging).
  * The nine result arrays come back as ONE device-to-host copy into a pinned mirror and are then copied out on the host.
- * Synchronous: the result arrays are complete when the call returns.  Calls are serialised inside the library.
+ * Synchronous: the result arrays are complete when the call returns.  Calls on the same device are serialised inside
+ * the library (they share the cached buffers); calls on different devices run concurrently (one host thread per GPU).
+ * On failure nothing of the call is left in flight: both streams are drained before the call returns, and after a
+ * CUDA error the cached state of that device is dropped and rebuilt by the next call.
  */
 int ft8b_decode_slots_host(const void *wave, int wave_dtype, int64_t n_slots, int64_t n_samples, int64_t slot_stride,
                            const ft8b_decode_params *p, int device, int64_t piece_slots, int32_t *cand_time, int32_t *cand_freq,
                            double *cand_score, int32_t *n_cand, uint8_t *ok, int32_t *ldpc_errors,
                            int32_t *crc_extracted, int32_t *crc_calculated, uint8_t *payload);
-/* Device-side duration (CUDA events: first copy enqueued .. last result byte on the host) of the most recent
- * ft8b_decode_slots_host call of this process, in ms. */
+/* Device-side duration (CUDA events: first copy enqueued .. last result byte on the host) of the calling thread's
+ * most recent successful ft8b_decode_slots_host call, in ms. */
 double ft8b_last_host_call_ms(void);
 /* Host threads that gather pageable caller memory into the pinned staging buffers of ft8b_decode_slots_host
  * (persistent, created on first use, the calling thread included in the count).  threads <= 0: the default

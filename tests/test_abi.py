@@ -63,6 +63,23 @@ def test_workspace_query_is_host_only():
     assert _lib.lib().ft8b_decode_workspace_bytes(C.byref(bad), 64, 180000) < 0
 
 
+@pytest.mark.parametrize("chunk", [0, 1, 7, 16, 64, 100, 2045])
+def test_workspace_bytes_bound_every_shorter_batch(chunk):
+    """ft8b_decode_workspace_bytes(n) is an upper bound for every batch of at most n slots (the host path sizes its
+    workspace once, for a full piece, and then decodes a shorter tail piece with it: with chunk_slots = 100 a 128-slot
+    piece runs as 2 x 64 but a 72..100-slot tail as ONE chunk).  Host-only query, so it is checked here."""
+    from ft8_demodulator_b200 import engine
+    p = engine.make_params(12000, 2, 2, 20, 1, 20, 0, 1920, 0, 186, chunk)
+    q = lambda n: int(_lib.lib().ft8b_decode_workspace_bytes(C.byref(p), n, 180000))
+    sizes = [q(n) for n in range(0, 300)] + [q(3000), q(4096)]
+    assert all(b >= a for a, b in zip(sizes, sizes[1:])), "not monotone in n_slots"
+    per_slot = 8 * (186 * 1920 + 88 * 1906)
+    lim = chunk if chunk else 2045
+    for n in (1, 64, 72, 100, 128, 299, 3000, 4096):
+        # room for the largest chunk a batch of <= n slots can be cut into, plus the LLRs of all its candidates
+        assert q(n) >= per_slot * min(lim, n) + 8 * 174 * 20 * n
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
 def test_no_cpu_fallback():
     from ft8_demodulator_b200.ft8_demodulator import ft8_decode as fd, ldpc_decoder as ld, spectrogram_analyse as sa

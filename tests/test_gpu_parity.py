@@ -170,6 +170,43 @@ def test_selection_vs_oracle_on_oracle_spectrogram(orc, c1_slot, K, thr):
     np.testing.assert_allclose(gs[0, :n].cpu().numpy(), cs, rtol=0, atol=1e-12)
 
 
+@pytest.mark.parametrize("K,thr", [(20, 1.0), (20, 3.0), (1, 1.0), (300, 2.5), (4096, 1.0), (50, -100.0)])
+def test_find_candidates_scores_bit_exact(orc, c1_slot, K, thr):
+    """ft8b_find_candidates (selection with the spectrogram at hand, what ft8b_decode_slots uses): on the same float64
+    spectrogram the returned scores are the reference's running sums BIT FOR BIT, not just within 1e-12."""
+    mag = orc.spectrogram_pos(c1_slot, 12000, 2, 2)
+    ct, cf, cs, npass = orc.ft8_find_candidates(mag, 2, 2, K, thr)
+    m = engine._dev(np.ascontiguousarray(mag.T).reshape(1, 186, 1920))
+    scores, t0 = engine.sync_scores(m, 2, 2)
+    gt, gf, gs, gn, gp = engine.select_candidates(scores, t0, K, thr, mag=m, time_osr=2, freq_osr=2)
+    n = int(gn.cpu()[0])
+    assert n == len(ct) and int(gp.cpu()[0]) == npass
+    assert gt[0, :n].cpu().numpy().tolist() == ct.tolist() and gf[0, :n].cpu().numpy().tolist() == cf.tolist()
+    assert np.array_equal(gs[0, :n].cpu().numpy(), cs)
+
+
+def test_find_candidates_threshold_decided_on_reference_sum(orc, c1_slot):
+    """A threshold placed exactly ON a score of the map (and one ulp above / below it): the fast kernels' score for that
+    cell differs from the reference's running sum in the last bits, so only the re-evaluation in the reference's
+    summation order makes the pass/skip decision - and with it the whole first-K list - come out as the reference's."""
+    mag = orc.spectrogram_pos(c1_slot, 12000, 2, 2)
+    ref_map = orc.score_map(mag, 2, 2)                        # reference running sums, [nt, nf]
+    m = engine._dev(np.ascontiguousarray(mag.T).reshape(1, 186, 1920))
+    scores, t0 = engine.sync_scores(m, 2, 2)
+    fast = scores[0].cpu().numpy()
+    head = ref_map[0, :200]
+    differing = [i for i in range(200) if np.isfinite(head[i]) and fast[0, i] != head[i] and head[i] > 0.5]
+    assert differing, "expected some head scores to differ in the last bits between the two summation orders"
+    for i in differing[:6]:
+        for thr in (head[i], np.nextafter(head[i], np.inf), np.nextafter(head[i], -np.inf)):
+            ct, cf, cs, npass = orc.ft8_find_candidates(mag, 2, 2, 20, float(thr))
+            gt, gf, gs, gn, _ = engine.select_candidates(scores, t0, 20, float(thr), mag=m, time_osr=2, freq_osr=2)
+            n = int(gn.cpu()[0])
+            assert n == len(ct)
+            assert gt[0, :n].cpu().numpy().tolist() == ct.tolist() and gf[0, :n].cpu().numpy().tolist() == cf.tolist()
+            assert np.array_equal(gs[0, :n].cpu().numpy(), cs)
+
+
 def test_selection_synthetic_maps():
     """Selection semantics on hand-made score maps (first-K + record replacement, K > passers, none)."""
     nt, nf = 6, 50
@@ -781,6 +818,48 @@ def test_host_abi_path_without_torch_tensors():
     rc = _lib.lib().ft8b_decode_slots_host(d.data_ptr(), _lib.DTYPE_F32, B, x.shape[1], x.shape[1], C.byref(prm), -1, 0, p(ct),
                                            p(cf), p(cs), p(nc), p(ok), p(le), p(ce), p(cc), p(pl))
     assert rc == _lib.ERR_ARG
+
+
+def test_host_abi_ragged_tail_with_small_chunks():
+    """A tail piece shorter than the piece can need a LARGER chunk than the full pieces did (chunk_plan balances:
+    piece 8 with chunk_slots 6 runs as 2 x 4, a 5- or 6-slot tail as one chunk of 5 / 6): the workspace sized for the
+    piece must serve the tail.  Also: crc_extracted / crc_calculated may be NULL on the host entry."""
+    import ctypes as C
+    from ft8_demodulator_b200 import _lib
+    kw = dict(bins_per_tone=2, steps_per_symbol=2, max_candidates=20, min_score=1, max_iterations=20)
+    x = np.stack([synth.c3_slot(i)[0] for i in range(14)]).astype(np.float32)
+    ref = fd.decode_slots(torch.from_numpy(x).cuda(), 12000, return_device=True, **kw)
+    for n, piece, chunk in [(14, 8, 6), (13, 8, 6), (11, 8, 5), (14, 8, 3), (7, 4, 3), (14, 12, 7)]:
+        got = fd.decode_slots(x[:n], 12000, piece_slots=piece, chunk_slots=chunk, **kw)
+        assert _same_decodes(got.arrays, engine.slice_slot_decodes(ref, 0, n)), (n, piece, chunk)
+    # NULL crc arrays through the raw host entry
+    g = fd.decode_geometry(x.shape[1], 12000, 2, 2, None, None, None, None)
+    prm = engine.make_params(12000, 2, 2, 20, 1, 20, g["bin_lo"], g["bin_hi"], g["frame_lo"], g["frame_hi"])
+    B, K = 3, 20
+    ct, cf, nc = np.zeros((B, K), np.int32), np.zeros((B, K), np.int32), np.zeros(B, np.int32)
+    cs, ok, le = np.zeros((B, K), np.float64), np.zeros((B, K), np.uint8), np.zeros((B, K), np.int32)
+    pl = np.zeros((B, K, 10), np.uint8)
+    p = lambda a: a.ctypes.data
+    rc = _lib.lib().ft8b_decode_slots_host(p(x), _lib.DTYPE_F32, B, x.shape[1], x.shape[1], C.byref(prm), -1, 0, p(ct), p(cf),
+                                           p(cs), p(nc), p(ok), p(le), None, None, p(pl))
+    assert rc == 0, _lib.lib().ft8b_last_error()
+    r3 = engine.slice_slot_decodes(ref, 0, 3).cpu()
+    assert np.array_equal(ct, r3.cand_time.numpy()) and np.array_equal(ok, r3.ok.numpy())
+    assert np.array_equal(pl, r3.payload.numpy()) and np.array_equal(le, r3.ldpc_errors.numpy())
+
+
+def test_empty_search_defines_every_output():
+    """'Nothing to search' (K = 0 is separate; here a band of 10 bins: fewer than 7 tones wide) returns zeros in all nine
+    output arrays of ft8b_decode_slots, not whatever the caller's buffers held."""
+    x = torch.from_numpy(np.stack([synth.c3_slot(i)[0] for i in range(2)]).astype(np.float32)).cuda()
+    prm = engine.make_params(12000, 2, 2, 20, 1, 20, 100, 110, 0, 186)
+    dec = engine.SlotDecoder(2, x.shape[1], prm, device=x.device)
+    for f in dec.out.__dataclass_fields__:
+        getattr(dec.out, f).fill_(77)
+    dec.run(x)
+    torch.cuda.synchronize()
+    for f in dec.out.__dataclass_fields__:
+        assert int(getattr(dec.out, f).abs().sum()) == 0, f
 
 
 def test_non_finite_audio_is_contained():
