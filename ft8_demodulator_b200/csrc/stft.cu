@@ -458,6 +458,11 @@ int stft_db(const void *wave, int wave_dtype, int64_t n_slots, int64_t n_samples
         // the staged path copies sample pairs with cp.async: every frame start must be pair aligned
         const size_t pair_bytes = wave_dtype == FT8B_DTYPE_F32 ? 8 : (wave_dtype == FT8B_DTYPE_I16 ? 4 : 16);
         const bool vec = (reinterpret_cast<uintptr_t>(wave) % pair_bytes == 0) && (slot_stride % 2 == 0) && (hop % 2 == 0);
+        {
+            const size_t eb = pair_bytes / 2;
+            f.copy16 = vec && (reinterpret_cast<uintptr_t>(wave) % 16 == 0) && ((slot_stride * eb) % 16 == 0) &&
+                       (((size_t)hop * eb) % 16 == 0);
+        }
 #define FT8B_STFT1920(T, MB)                                                                              \
     do {                                                                                                  \
         if (vec) stft1920_kernel<T, MB, true><<<(unsigned)g1920, kStft1920Threads, stft1920_smem_bytes<T, true>(), stream>>>(f);   \

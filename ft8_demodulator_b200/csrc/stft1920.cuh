@@ -46,6 +46,7 @@ struct Stft1920Args {
     int bin_lo, bin_hi;
     int64_t frame_lo, frames_out;
     double *mag;
+    int copy16;               // every frame starts on a 16-byte boundary: stage it with 16-byte cp.async.cg
 };
 
 namespace f1920 {
@@ -69,6 +70,7 @@ __device__ __constant__ double kK[40] = {
     /* 20 */ 1.4476482397306845, /* 21 */ -2.1714723595960267, /* 22 */ 4.3429448190325183,
     /* 23 */ 3.0102999566398120,      // 10*log10(2)
     /* 24 */ 1e-12,
+    /* 25 */ 1e-300,                  // fast_db: carries inf / NaN into the result, vanishes for finite powers
 };
 
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
@@ -212,20 +214,24 @@ __device__ __forceinline__ void bf8(double2 (&a)[8]) {
 // `tab` is this lane's view of the shared table: 8 interleaved copies, entry i of copy q at tab8[i*8 + q], so the
 // 8 lanes of a quarter-warp (one 128-byte shared-memory wavefront for 16-byte loads) never collide.
 __device__ __forceinline__ double fast_db(double v, const double2 *__restrict__ tab) {
-    // branch-free: inf / NaN inputs (never produced by finite audio) are patched in at the end with selects
-    const long long bits = __double_as_longlong(v);
-    const int e = (int)(bits >> 52) - 1023;
-    const int i = (int)(bits >> 46) & 63;
-    const double m = __longlong_as_double((bits & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);
-    const double2 t = tab[i * 8];
+    // Branch-free and select-free.  inf / NaN inputs (never produced by finite audio) reach the result through the
+    // term v * 1e-300: for every finite power it is below half an ulp of the table value it is added to (v < 1e280 -
+    // float32 audio cannot exceed 1e90) and changes nothing; +inf stays +inf and NaN stays NaN, as 10*log10 would give
+    // (one DFMA instead of the compare, the v + v and the two selects that used to patch them in: -3 instructions per bin).
+    const unsigned hi = (unsigned)__double2hiint(v);
+    const int e = (int)(hi >> 20) - 1023;
+    // entry i = top 6 mantissa bits of this lane's copy: byte offset i * 128 = (hi >> 7) & 0x1f80 (one shift, one mask, one add)
+    const double2 t = *reinterpret_cast<const double2 *>(reinterpret_cast<const char *>(tab) + ((hi >> 7) & 0x1f80u));
+    unsigned mh;                                    // (hi & 0xfffff) | 0x3ff00000 as ONE three-input logic op
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(mh) : "r"(hi), "r"(0x000fffffu), "r"(0x3ff00000u));
+    const double m = __hiloint2double((int)mh, __double2loint(v));
     const double r = fma(m, t.x, -1.0);
     double p = kK[18];                              //  (10/ln10)/5
     p = fma(p, r, kK[19]);                          // -(10/ln10)/4
     p = fma(p, r, kK[20]);                          //  (10/ln10)/3
     p = fma(p, r, kK[21]);                          // -(10/ln10)/2
     p = fma(p, r, kK[22]);                          //  (10/ln10)
-    const double res = fma(r, p, fma((double)e, kK[23], t.y));
-    return (__double2hiint(v) >= 0x7ff00000) ? v + v : res;  // +inf -> +inf, NaN -> NaN (as 10*log10 would); v > 0
+    return fma(r, p, fma((double)e, kK[23], fma(v, kK[25], t.y)));
 }
 
 // Untangle the pair (Z[k], Z[M-k]) of the packed transform into dB for bins k and M-k
@@ -236,9 +242,8 @@ __device__ __forceinline__ void untangle_pair(double2 z, double2 zr, double2 w, 
     // scale4 = scale/4: scaling by a power of two commutes with rounding, so the dB values are the same bit for bit.
     // The contractions are spelled out so that the full-band and the cropped store paths (two inlined copies of this
     // code) round the same way: their outputs are compared bit for bit.
-    const double2 zc = make_double2(zr.x, -zr.y);
-    const double2 e = cadd(z, zc);
-    const double2 d = csub(z, zc);
+    const double2 e = make_double2(z.x + zr.x, z.y - zr.y);      // z + conj zr
+    const double2 d = make_double2(z.x - zr.x, z.y + zr.y);      // z - conj zr
     const double2 p = make_double2(fma(w.x, d.x, -__dmul_rn(w.y, d.y)), fma(w.x, d.y, __dmul_rn(w.y, d.x)));
     const double re1 = e.x + p.y, im1 = e.y - p.x;
     const double re2 = e.x - p.y, im2 = e.y + p.x;
@@ -276,7 +281,7 @@ __device__ __forceinline__ double to_sample(double v) { return v; }
 __device__ __forceinline__ double to_sample(short v) { return from_pcm16(v); }
 
 #ifndef FT8B_STFT_SMEMTAB
-#define FT8B_STFT_SMEMTAB 0
+#define FT8B_STFT_SMEMTAB 1      // P3 twiddles + post-twiddles in shared memory (7.93 -> 7.81 ms per 4096 slots; 0 = __ldg from L1)
 #endif
 constexpr int kTw3Cols = 121;       // columns 0..120 of tw3 are the only ones P3 touches
 constexpr int kTwpLen = 481;        // post-twiddles 0..480; 481..960 follow from W^k = -i conj(W^(960-k))
@@ -325,6 +330,42 @@ __global__ void __launch_bounds__(kStft1920Threads, MB) stft1920_kernel(const St
         const int64_t sl = it / a.frames_out;
         return reinterpret_cast<const WaveT *>(a.wave) + sl * a.slot_stride + (it - sl * a.frames_out + a.frame_lo) * a.hop;
     };
+#ifndef FT8B_STFT_STAGE16
+#define FT8B_STFT_STAGE16 1
+#endif
+#if FT8B_STFT_STAGE16
+    // The next frame's 1920 samples are copied into `xs` with cp.async right after this frame's P1 has read the buffer,
+    // and waited for just before the barrier that separates P2 from P3 - a whole radix-16 pass later, so the wait costs
+    // nothing, and the barrier that is there anyway makes every thread's copies visible to all.  P1 of the next frame
+    // then starts without a wait.  Frames that start on a 16-byte boundary are copied 16 bytes at a time with
+    // cp.async.cg (no L1 allocation: the audio stream does not evict the window and twiddle tables); others pair by pair.
+    auto stage_audio = [&](int64_t it) {
+        if (VEC && it < n_items) {
+            const char *src = reinterpret_cast<const char *>(frame_audio(it));
+            if (a.copy16) {
+                constexpr int n16 = (int)sizeof(WaveT) * kM1920 / 16;
+#pragma unroll
+                for (int t = 0; t < (n16 + 127) / 128; ++t) {
+                    const int c = tid + 128 * t;
+                    if (c < n16)
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(reinterpret_cast<char *>(xs) + 16 * c)),
+                                     "l"(src + 16 * c) : "memory");
+                }
+            } else {
+                constexpr int kPair = 2 * (int)sizeof(WaveT);
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    const int n = tid + 128 * t;
+                    if (t < 7 || tid < 64) __pipeline_memcpy_async(reinterpret_cast<char *>(xs) + kPair * n, src + kPair * n, kPair);
+                }
+            }
+        }
+        __pipeline_commit();
+    };
+    stage_audio(blockIdx.x);
+    if (VEC) __pipeline_wait_prior(0);
+    __syncthreads();
+#else
     // Each thread copies exactly the sample pairs it will consume in P1 (n = tid + 128 t), so waiting on its own
     // cp.async groups is enough - no block barrier guards the staging buffer.
     auto stage_audio = [&](int64_t it) {
@@ -341,13 +382,16 @@ __global__ void __launch_bounds__(kStft1920Threads, MB) stft1920_kernel(const St
     };
     stage_audio(blockIdx.x);
     __syncthreads();
+#endif
     FT8B_PROF_DECL
     for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int64_t slot = item / a.frames_out;
         const int64_t fr = item - slot * a.frames_out;
         const WaveT *x = VEC ? xs : frame_audio(item);
         double *out = a.mag + (slot * a.frames_out + fr) * (int64_t)Fout;
+#if !FT8B_STFT_STAGE16
         if (VEC) __pipeline_wait_prior(0);     // this thread's pairs of this frame have landed
+#endif
         FT8B_PROF(0);
         // ---------------- P1: radix 15, inputs z[j + 128 t] = (w x)[2n] + i (w x)[2n+1], zero for n >= 960
         {
@@ -406,6 +450,9 @@ __global__ void __launch_bounds__(kStft1920Threads, MB) stft1920_kernel(const St
             }
         }
         FT8B_PROF(3);
+#if FT8B_STFT_STAGE16
+        if (VEC) __pipeline_wait_prior(0);     // the next frame's audio (staged after P1) has landed: visible to all after the barrier
+#endif
         __syncthreads();
         FT8B_PROF(4);
         // ---------------- P3: radix 8, Ns = 240, paired butterflies + untangling + dB store
@@ -433,7 +480,7 @@ __global__ void __launch_bounds__(kStft1920Threads, MB) stft1920_kernel(const St
                 const double2 w = __ldg(&a.tw3[t * kTw3Stride + j1]);
 #endif
                 u1[t] = cmul(u1[t], w);
-                u2[t] = cmul(u2[t], make_double2(w.x, -w.y));
+                u2[t] = make_double2(u2[t].x * w.x + u2[t].y * w.y, u2[t].y * w.x - u2[t].x * w.y);   // * conj w
             }
             bf8(u1);
             bf8(u2);

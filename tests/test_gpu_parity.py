@@ -118,6 +118,26 @@ def test_stft_signal_floor():
     assert torch.all(scores == 0.0)
 
 
+def test_stft_non_finite_audio_stays_non_finite():
+    """inf / NaN samples: every frame that contains one comes out non-finite in every bin (never a finite garbage dB
+    value the Costas search could score); frames that do not contain it are untouched."""
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal(20000)
+    ref = gpu_mag(x, 12000, 2, 2)
+    for bad in (np.inf, -np.inf, np.nan):
+        y = x.copy()
+        y[5000] = bad                       # frames 4 and 5 (hop 960, window 1920) contain sample 5000
+        got = gpu_mag(y.astype(np.float32), 12000, 2, 2)[0]
+        hit = [j for j in range(got.shape[0]) if 960 * j <= 5000 < 960 * j + 1920]
+        assert hit == [4, 5]
+        for j in range(got.shape[0]):
+            if j in hit:
+                assert not torch.isfinite(got[j]).any(), (bad, j)
+            else:
+                assert torch.isfinite(got[j]).all()
+    assert torch.isfinite(ref).all()
+
+
 def test_calculate_spectrogram_dropin(c1_slot):
     g = load_golden("c1.npz")
     S, f, t = sa.calculate_spectrogram(c1_slot, 12000, 2, 2)
