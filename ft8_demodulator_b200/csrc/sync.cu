@@ -248,6 +248,7 @@ __global__ void __launch_bounds__(kSyncThreads) sync_scores_kernel(const SyncArg
 }  // namespace ft8b
 
 #include "sync_pair.cuh"
+#include "sync_lap.cuh"
 
 namespace ft8b {
 
@@ -730,6 +731,15 @@ __global__ void __launch_bounds__(kSelThreads) select_topk_kernel(const SelArgs 
 }
 
 // ------------------------------------------------------------------------------------------
+// FT8B_SYNC_LAP=1: freq_osr 2 runs on the path-sum Laplacian kernel (sync_lap.cuh) instead of the difference walk of
+// sync_pair.cuh.  An independent formulation of the same map (40 % fewer float64 additions, but more shared-memory /
+// shuffle traffic and 15 % more warp-steps: 5.79 ms against 5.19 ms per 4096 slots, so it is not the default); kept as
+// the cross-check of the walk in the tests.
+static bool sync_uses_lap(int b) {
+    const char *env_lap = getenv("FT8B_SYNC_LAP");
+    return b == 2 && env_lap && env_lap[0] == '1';
+}
+
 // strips per slot the pair kernels summarise (0 when the geometry runs on sync_scores_kernel, which does not)
 int sync_tiles_per_slot(int T, int F, int s, int b) {
     int t0, nt, nf;
@@ -739,6 +749,7 @@ int sync_tiles_per_slot(int T, int F, int s, int b) {
     if (nt <= 0 || nf <= 0 || !(b == 1 || b == 2 || b == 4) || (env_single && env_single[0] == '1') ||
         (env_scan && env_scan[0] == '1'))
         return 0;
+    if (sync_uses_lap(b)) return s * ((sync_lap_warps(nf) + 1) / 2) * (kLapThreads / 32);
     return s * ((nf + kPairCols - 1) / kPairCols) * (kPairThreads / 32);
 }
 
@@ -763,6 +774,25 @@ int sync_scores(const double *mag, int64_t n_slots, int T, int F, int s, int b, 
     const char *env_single = getenv("FT8B_SYNC_SINGLE");            // "1": one candidate per thread for every freq_osr
     const bool single = env_single && env_single[0] == '1';
     const bool pair = (b == 1 || b == 2 || b == 4) && !single;      // two candidates per thread (sync_pair.cuh)
+    if (pair && sync_uses_lap(b)) {
+        const size_t smem_l = sync_lap_smem_bytes(a.nu);
+        if (smem_l > (size_t)max_smem) {
+            set_error("ft8b_sync_scores: %d time offsets per phase need %zu bytes of shared memory (limit %d)", a.nu, smem_l, max_smem);
+            return FT8B_ERR_UNSUPPORTED;
+        }
+        dim3 grid((sync_lap_warps(nf) + 1) / 2, s, (unsigned)n_slots);
+#define FT8B_LAP_LAUNCH(TR, NBC)                                                                                                 \
+    do {                                                                                                                         \
+        FT8B_CUDA_TRY(cudaFuncSetAttribute(sync_scores_lap_kernel<TR, NBC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem)); \
+        sync_scores_lap_kernel<TR, NBC><<<grid, kLapThreads, smem_l, stream>>>(a);                                               \
+    } while (0)
+        // 93 symbol columns per phase = a 15-s slot at any sample rate (186 frames, time_osr 2): unrolled head / tail
+        if (a.nb == 93) { if (tiles) FT8B_LAP_LAUNCH(true, 93); else FT8B_LAP_LAUNCH(false, 93); }
+        else            { if (tiles) FT8B_LAP_LAUNCH(true, 0); else FT8B_LAP_LAUNCH(false, 0); }
+#undef FT8B_LAP_LAUNCH
+        FT8B_LAUNCH_CHECK("sync_scores_lap_kernel");
+        return 0;
+    }
     const size_t smem = pair ? (b == 1 ? sync_pair_smem_bytes<1>(a.nu) : b == 2 ? sync_pair_smem_bytes<2>(a.nu) : sync_pair_smem_bytes<4>(a.nu))
                              : sizeof(double) * ((size_t)a.nu * kSyncThreads + (size_t)(kSyncThreads / 32) * kSyncStages * (32 + 7 * b)) +
                                    sizeof(double2) * (size_t)a.nu;

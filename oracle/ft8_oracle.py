@@ -130,6 +130,74 @@ def score_map(mag, tosr, fosr):
     return out
 
 
+def score_map_laplacian(mag, tosr, fosr):
+    """The reference's score map (ft8_sync_score over ft8_find_candidates' ranges, ft8_decode.py:47-124) restated as a
+    Laplacian of Costas PATH SUMS - the formulation csrc/sync_lap.cuh computes (same terms, different association: it
+    agrees with score_map(), the reference-pinned running sum, to ~1e-14, not bit for bit; tests/test_oracle_golden.py).
+
+    Per oversampling phase, with A[g][bin] the phase's columns and columns outside [0, nb) contributing nothing:
+        P[h](f)  = sum_k A[h+k][f + b*C[k]]                       plain sum of the 7 cells of block h
+        B[h](f)  = 4 P[h](f) - P[h](f+b) - P[h](f-b) - P[h-1](f) - P[h+1](f) + Corr[h](f)
+        Corr[h]  = A[h+3][f-b] - A[h+3][f]                        tone 0 (k = 3) has no lower neighbour
+                 + A[h-1][c0]  - A[h][c0]                         k = 0 has no earlier neighbour
+                 + A[h+7][c6]  - A[h+6][c6]                       k = 6 has no later neighbour
+                 + A[0][c(j-1)] - A[0][c(j)]        (h = -j, j = 1..6)       block cut by the first column
+                 + A[nb-1][c(k+1)] - A[nb-1][c(k)]  (h = nb-1-k, k = 0..5)   block cut by the last column
+        score(u, f) = (B[u-10] + B[u+26] + B[u+62]) / num_comparisons(u)
+    mag [F, T] as elsewhere in this module.  NumPy, vectorised over frequency."""
+    m = _f64(mag)
+    F, T = m.shape
+    s, b = tosr, fosr
+    nb = T // s
+    t0, t1, f0, f1 = search_ranges(F, T, s, b)
+    nt, nf = max(t1 - t0, 0), max(f1 - f0, 0)
+    out = np.full((nt, nf), -np.inf)
+    if nt == 0 or nf == 0:
+        return out
+    Cp = [3, 1, 4, 0, 6, 5, 2]
+    nu = nt // s
+    pad = 2 * b
+    f = np.arange(nf)
+    fr = np.arange(-b, nf + b)                              # candidates including one tone of halo on both sides
+    for rho in range(s):
+        A = m[:, rho::s][:, :nb].T
+        Ap = np.zeros((nb, F + 2 * pad))
+        Ap[:, pad:pad + F] = A
+        Ap[:, :pad] = A[:, :1]                              # bins outside the row: any finite value (they cancel)
+        Ap[:, pad + F:] = A[:, -1:]
+
+        def a(g, bins):
+            return Ap[g, bins + pad] if 0 <= g < nb else np.zeros(len(bins))
+
+        P = {h: sum(a(h + k, fr + b * Cp[k]) for k in range(7)) for h in range(-8, nb + 2)}
+        B = {}
+        for h in range(-7, nb):
+            corr = a(h + 3, f - b) - a(h + 3, f)
+            corr = corr + a(h - 1, f + b * Cp[0]) - a(h, f + b * Cp[0])
+            corr = corr + a(h + 7, f + b * Cp[6]) - a(h + 6, f + b * Cp[6])
+            if -6 <= h <= -1:
+                corr = corr + a(0, f + b * Cp[-h - 1]) - a(0, f + b * Cp[-h])
+            if nb - 6 <= h <= nb - 1:
+                k = nb - 1 - h
+                corr = corr + a(nb - 1, f + b * Cp[k + 1]) - a(nb - 1, f + b * Cp[k])
+            ctr, up, dn = slice(b, b + nf), slice(2 * b, 2 * b + nf), slice(0, nf)
+            B[h] = 4 * P[h][ctr] - P[h][up] - P[h][dn] - P[h - 1][ctr] - P[h + 1][ctr] + corr
+        for u in range(nu):
+            tot, ncmp = np.zeros(nf), 0
+            for mm in range(3):
+                h = u - 10 + 36 * mm
+                if h in B:
+                    tot = tot + B[h]
+                for k in range(7):
+                    g = h + k
+                    if 0 <= g < nb:
+                        ncmp += (Cp[k] > 0) + 1 + (1 if (k > 0 and g > 0) else 0) + (1 if (k < 6 and g + 1 < nb) else 0)
+            with np.errstate(all="ignore"):
+                row = tot / ncmp if ncmp > 0 else np.full(nf, -np.inf)
+            out[u * s + rho] = np.where(np.isfinite(row), row, -np.inf)
+    return out
+
+
 def score_map_drift(mag, tosr, fosr, drift_bins_per_symbol):
     """CPU statement of the drift-hypothesis Costas search (an EXTENSION of the new repo: BASELINE north_star names it
     for the satellite path, the reference has no counterpart - parity unpinned; with the single hypothesis 0.0 it is

@@ -116,6 +116,10 @@ def test_stft_signal_floor():
     assert torch.all(got == got.flatten()[0])
     scores, _ = engine.sync_scores(gpu_mag(np.zeros(180000), 12000, 2, 2), 2, 2)
     assert torch.all(scores == 0.0)
+    # ... and what the search returns for silence is the reference's exact 0 (threshold on the score itself included)
+    res = fd.decode_slots(np.zeros((1, 180000), dtype=np.float32), 12000, 2, 2, max_candidates=20, min_score=0, max_iterations=2)
+    assert int(res.arrays.n_cand[0]) == 20 and torch.all(res.arrays.cand_score[0] == 0.0)
+    assert res.arrays.cand_time[0].tolist() == [-20] * 20 and res.arrays.cand_freq[0].tolist() == list(range(20))
 
 
 def test_stft_non_finite_audio_stays_non_finite():
@@ -693,6 +697,53 @@ def test_sync_pair_kernel_equals_single_kernel(monkeypatch, b, s, F, T):
     monkeypatch.delenv("FT8B_SYNC_SINGLE")
     assert pair.shape == single.shape and pair.numel() > 0
     assert torch.equal(pair.view(torch.int64), single.view(torch.int64))
+
+
+@pytest.mark.parametrize("s,F,T", [(2, 1920, 186), (2, 961, 186), (1, 500, 93), (3, 333, 300), (2, 75, 120), (4, 130, 411),
+                                   (2, 61 + 14, 110), (2, 60 + 14, 110), (2, 121 + 14, 110)])
+def test_sync_laplacian_kernel_vs_walk_and_oracle(orc, monkeypatch, s, F, T):
+    """freq_osr 2: the path-sum Laplacian kernel (sync_lap.cuh, FT8B_SYNC_LAP=1 - an independent formulation of the score
+    map, not the default) against the difference walk (sync_pair.cuh) and against the oracle's reference-order map.  Same
+    terms in a different association: 1e-12 on dB-scale waterfalls, identical -inf pattern (non-finite cells, offsets
+    without comparisons); widths around the 60-candidate strips of the kernel; 93 columns per phase (unrolled tail) and
+    other lengths (rolled tail).  The whole pipeline on top of it returns the same candidates and decodes."""
+    g = torch.Generator(device="cuda").manual_seed(F * 3 + T + s)
+    mag = torch.randn((3, T, F), device="cuda", dtype=torch.float64, generator=g) * 6 - 60
+    mag[1, 5, 7] = float("inf")
+    mag[2, 40:44, :] = float("nan")
+    walk, t0 = engine.sync_scores(mag, s, 2)
+    monkeypatch.setenv("FT8B_SYNC_LAP", "1")
+    lap, _ = engine.sync_scores(mag, s, 2)
+    monkeypatch.delenv("FT8B_SYNC_LAP")
+    assert lap.shape == walk.shape and lap.numel() > 0
+    # finite waterfall (slot 0): identical -inf pattern.  Non-finite cells (slots 1, 2): every score the reference voids
+    # is void here too, plus a few whose path sums merely pass through the bad cell and cancel it algebraically
+    # (inf - inf): one more reason this kernel is a cross-check, not the default.
+    assert torch.equal(torch.isneginf(lap[0]), torch.isneginf(walk[0]))
+    assert torch.all(torch.isneginf(lap) | ~torch.isneginf(walk))
+    fin = torch.isfinite(walk) & torch.isfinite(lap)
+    assert (lap[fin] - walk[fin]).abs().max().item() < 1e-12
+    ref = orc.score_map(np.ascontiguousarray(mag[0].cpu().numpy().T), s, 2)
+    assert np.abs(lap[0].cpu().numpy() - ref).max() < 1e-12
+    # a constant waterfall (digital silence): exactly 0 wherever the three blocks and their time neighbours are complete
+    const = torch.full((1, T, F), -120.00000000000001, dtype=torch.float64, device="cuda")
+    monkeypatch.setenv("FT8B_SYNC_LAP", "1")
+    z, _ = engine.sync_scores(const, s, 2)
+    monkeypatch.delenv("FT8B_SYNC_LAP")
+    nb = T // s
+    rows = [u * s + r for u in range(11, max(11, nb - 69)) for r in range(s) if u * s + r < z.shape[1]]
+    assert z.abs().max().item() < 1e-12 and (not rows or torch.all(z[0, rows] == 0.0))
+
+
+def test_pipeline_on_laplacian_kernel_equals_default(monkeypatch):
+    kw = dict(bins_per_tone=2, steps_per_symbol=2, max_candidates=20, min_score=1, max_iterations=20)
+    x = np.stack([synth.c3_slot(i)[0] for i in range(6)]).astype(np.float32)
+    ref = fd.decode_slots(x, 12000, **kw).arrays
+    monkeypatch.setenv("FT8B_SYNC_LAP", "1")
+    got = fd.decode_slots(x, 12000, **kw).arrays
+    monkeypatch.delenv("FT8B_SYNC_LAP")
+    for f in ref.__dataclass_fields__:
+        assert torch.equal(getattr(got, f), getattr(ref, f)), f
 
 
 @pytest.mark.parametrize("K,thr", [(20, 1.0), (20, 4.0), (3, -5.0), (1, 1.0), (64, 2.5), (20, 50.0)])

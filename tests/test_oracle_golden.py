@@ -152,3 +152,22 @@ def test_drift_statement_is_pinned_by_the_plain_score_map(orc, F, T, s, b):
     g3, h3 = orc.score_map_drift(mag, s, b, [0.0, 0.21, -0.21])
     assert (g3 >= ref).all() and set(np.unique(h3)) <= {0, 1, 2}
     assert np.array_equal(g3[h3 == 0], ref[h3 == 0])
+
+
+@pytest.mark.parametrize("F,T,s,b", [(1920, 186, 2, 2), (400, 186, 1, 2), (300, 190, 3, 1), (101, 200, 2, 2), (64, 120, 2, 4),
+                                     (257, 347, 4, 4), (120, 105, 2, 2)])
+def test_laplacian_statement_equals_running_sum_map(orc, F, T, s, b):
+    """The path-sum Laplacian form of the score map (what csrc/sync_lap.cuh computes) against the reference-pinned running
+    sum, including the time offsets whose Costas blocks are cut by the first / last column."""
+    rng = np.random.default_rng(F * 7 + T)
+    mag = rng.standard_normal((F, T)) * 6 - 60
+    ref = orc.score_map(mag, s, b)
+    got = orc.score_map_laplacian(mag, s, b)
+    assert got.shape == ref.shape and ref.size
+    fin = np.isfinite(ref)
+    assert np.array_equal(np.isfinite(got), fin)
+    assert np.abs(got[fin] - ref[fin]).max() < 1e-13
+    # digital silence: every comparison is exactly 0
+    const = np.full((F, T), -120.00000000000001)
+    z = orc.score_map_laplacian(const, s, b)
+    assert np.abs(z[np.isfinite(z)]).max() < 1e-12
