@@ -18,7 +18,7 @@
 //                                        has no earlier neighbour, and P[h+1] has one cell more in column 0
 //     + A[nb-1][c(k+1)] - A[nb-1][c(k)]  block cut by the last column (h = nb-1-k, k = 0..5), likewise
 // (each term only where its column exists).  A score is the sum of its three blocks divided by the comparison count.
-// oracle/ft8_oracle.py::score_map_laplacian states this in NumPy and tests/test_oracle_golden.py holds it to the
+// The CPU oracle states this in NumPy (score_map_laplacian) and tests/test_oracle_golden.py holds it to the
 // reference-pinned running-sum map (2e-14 on dB-scale waterfalls).
 //
 // Why.  The walk of sync_pair.cuh forms the four differences per cell: 31.6 float64 adds per (column, candidate).
