@@ -199,7 +199,8 @@ def measured_pipe_utilisation(stage):
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     try:
         d = json.load(open(p))[stage]
-        return {"fp64_pipe_pct": d["fp64_pipe_pct"], "issue_active_pct": d["issue_active_pct"], "dram_pct": d["dram_pct"]}
+        return {"fp64_pipe_pct": d["fp64_pipe_pct"], "issue_active_pct": d["issue_active_pct"], "dram_pct": d["dram_pct"],
+                "lsu_pipe_pct": d.get("lsu_pipe_pct")}
     except Exception:
         return None
 
@@ -376,6 +377,21 @@ def main():
                "identical_to_device_resident_run": bool(same),
                "pageable_numpy_input": {"value": world * B / dt_np, "unit": "slots/s", "identical": bool(same_np)},
                "torch_stream_overlap": {"value": world * B / dt_th, "unit": "slots/s", "identical": bool(same_th)}}
+        # the link itself: the same pinned batch copied host-to-device with nothing else going on (what bounds e2e)
+        dst = torch.empty_like(waves)
+        dst.copy_(host, non_blocking=True)
+        torch.cuda.synchronize()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(2):
+            dst.copy_(host, non_blocking=True)
+        c1.record()
+        torch.cuda.synchronize()
+        link_gbs = 2 * host.numel() * 4 / (c0.elapsed_time(c1) * 1e-3) / 1e9
+        del dst
+        e2e["h2d_link"] = {"plain_copy_gbs": link_gbs, "e2e_gbs": host.numel() * 4 * e2e_steps / dt / 1e9,
+                           "e2e_frac_of_plain_copy": (host.numel() * 4 * e2e_steps / dt / 1e9) / link_gbs,
+                           "note": "e2e moves 720 kB per slot over PCIe; a plain cudaMemcpyAsync of the same pinned batch is the ceiling"}
         del host
         # same call fed 16-bit PCM (what a WAV file / SDR capture holds; from_wave.py semantics): half the PCIe bytes.
         # Extra information only - the audio is a 16-bit quantisation of the batch, so results are not comparable
@@ -472,7 +488,7 @@ def main():
                                    if STAGES[dom] in SURVEY_FP32_BYTES else None),
             "avg_launch_ms": sm[dom] / max(sn[dom], 1),
             "ncu_utilisation": measured_pipe_utilisation(STAGES[dom]),
-            "note": "float64 FFT/stencil/BP kernels are bound by the FP64 pipe and shared memory, not HBM (DESIGN.md)"}
+            "note": "float64 FFT/stencil/BP kernels are bound by the shared-memory (LSU) data pipe and the FP64 pipe, not HBM (DESIGN.md)"}
 
     line = {
         "metric": "decoded 15-s FT8 slots/sec", "value": value, "unit": "slots/s", "n_gpus": world, "steps": args.steps,

@@ -540,10 +540,21 @@ __global__ void __launch_bounds__(THREADS) select_candidates_kernel(const SelArg
     if (mag) {
         const long long rec_i = s_rec_i;
         const int n_items = n_first + (rec_i != 0x7fffffffffffffffLL ? 1 : 0);
-        for (int it = wid; it < n_items; it += kSelWarps) {
-            const long long idx = (it < n_first) ? hi[it] : rec_i;
-            const double e = ref_sync_score_warp(mag, a.F, a.s, a.b, a.nb, a.t0 + (int)(idx / a.nf), (int)(idx % a.nf), lane);
-            if (lane == 0) {
+        if (THREADS <= 256) {
+            // short lists: one warp per score (latency of ONE score matters: 21 warps cover K = 20 in three rounds)
+            for (int it = wid; it < n_items; it += kSelWarps) {
+                const long long idx = (it < n_first) ? hi[it] : rec_i;
+                const double e = ref_sync_score_warp(mag, a.F, a.s, a.b, a.nb, a.t0 + (int)(idx / a.nf), (int)(idx % a.nf), lane);
+                if (lane == 0) {
+                    if (it < n_first) hs[it] = e; else s_rec_s = e;
+                }
+            }
+        } else {
+            // long lists (K up to 4096): one THREAD per score - 1024 running sums in flight hide each other's load
+            // latency (K = 2000: 63 warp rounds of ~6 us against two thread rounds)
+            for (int it = tid; it < n_items; it += kSelThreads) {
+                const long long idx = (it < n_first) ? hi[it] : rec_i;
+                const double e = ref_sync_score(mag, a.F, a.s, a.b, a.nb, a.t0 + (int)(idx / a.nf), (int)(idx % a.nf));
                 if (it < n_first) hs[it] = e; else s_rec_s = e;
             }
         }

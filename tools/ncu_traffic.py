@@ -35,6 +35,7 @@ for r in data:
               "dram_bytes_per_slot": (rd + wr) / slots,
               "fp64_pipe_pct": float(r[ix["sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"]]),
               "issue_active_pct": float(r[ix["smsp__issue_active.avg.pct_of_peak_sustained_active"]]),
+              "lsu_pipe_pct": float(r[ix["l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"]]),
               "dram_pct": float(r[ix["gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"]]),
               "duration_us_under_ncu": float(r[ix["gpu__time_duration.sum"]]) * (1e3 if units[ix["gpu__time_duration.sum"]] == "ms" else 1)}
 json.dump(res, open(out, "w"), indent=1, sort_keys=True)
