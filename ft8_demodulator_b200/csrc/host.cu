@@ -297,7 +297,7 @@ int host_call(HostPath &h, const HostCall &c) {
     const int64_t n_slots = c.n_slots, K = p->max_candidates;
     const size_t elt = c.wave_dtype == FT8B_DTYPE_F32 ? 4 : (c.wave_dtype == FT8B_DTYPE_I16 ? 2 : 8);
     const size_t row_bytes = (size_t)c.n_samples * elt, src_pitch = (size_t)c.slot_stride * elt;
-    const int64_t piece = std::min<int64_t>(n_slots, c.piece_slots > 0 ? c.piece_slots : 128);
+    const int64_t piece = std::min<int64_t>(n_slots, c.piece_slots > 0 ? c.piece_slots : 256);
     // ft8b_decode_workspace_bytes(piece) covers every batch of at most `piece` slots, i.e. the shorter tail piece too
     // (whose single chunk may be larger than the balanced chunks of a full piece)
     const int64_t work_need = ft8b_decode_workspace_bytes(p, piece, c.n_samples);
@@ -384,15 +384,31 @@ int host_call(HostPath &h, const HostCall &c) {
         if (rc) return rc;
         FT8B_CUDA_TRY(cudaEventRecord(h.done[k], h.compute));
     }
-    // results: one copy of the whole result block into the pinned mirror (nine copies into pageable caller arrays would
-    // each be staged and waited for by the driver), then plain memcpy into the caller's arrays
-    FT8B_CUDA_TRY(cudaMemcpyAsync(h.res_host, h.res, off[9], cudaMemcpyDeviceToHost, h.compute));
+    const size_t len[9] = {4 * nK, 4 * nK, 8 * nK, 4 * (size_t)n_slots, nK, 4 * nK, 4 * nK, 4 * nK, 10 * nK};
+    // Results.  Large result sets into page-locked caller arrays (a pinned torch tensor, cudaHostAlloc memory): nine
+    // device-to-host copies straight into them - no mirror, no host memcpy, no first-touch page faults on fresh
+    // destination pages (0.5 ms of a 4096-slot call).  Otherwise: ONE copy of the whole result block into the pinned
+    // mirror (nine copies into pageable arrays would each be staged and waited for by the driver, and nine copies of a
+    // single-slot result cost more than they save), then plain memcpy into the caller's arrays.
+    bool direct = off[9] >= (1u << 20);
+    for (int a = 0; a < 9 && direct; ++a) {
+        if (!c.dst[a] || !len[a]) continue;
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, c.dst[a]) != cudaSuccess) { cudaGetLastError(); direct = false; }
+        else if (at.type != cudaMemoryTypeHost) direct = false;
+    }
+    if (direct) {
+        for (int a = 0; a < 9; ++a)
+            if (len[a] && c.dst[a]) FT8B_CUDA_TRY(cudaMemcpyAsync(c.dst[a], h.res + off[a], len[a], cudaMemcpyDeviceToHost, h.compute));
+    } else {
+        FT8B_CUDA_TRY(cudaMemcpyAsync(h.res_host, h.res, off[9], cudaMemcpyDeviceToHost, h.compute));
+    }
     FT8B_CUDA_TRY(cudaEventRecord(h.t_end, h.compute));
     FT8B_CUDA_TRY(cudaStreamSynchronize(h.compute));
     FT8B_CUDA_TRY(cudaStreamSynchronize(h.copy));
-    const size_t len[9] = {4 * nK, 4 * nK, 8 * nK, 4 * (size_t)n_slots, nK, 4 * nK, 4 * nK, 4 * nK, 10 * nK};
-    for (int a = 0; a < 9; ++a)
-        if (len[a] && c.dst[a]) std::memcpy(c.dst[a], static_cast<const char *>(h.res_host) + off[a], len[a]);
+    if (!direct)
+        for (int a = 0; a < 9; ++a)
+            if (len[a] && c.dst[a]) std::memcpy(c.dst[a], static_cast<const char *>(h.res_host) + off[a], len[a]);
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, h.t_beg, h.t_end) == cudaSuccess) g_last_host_ms = ms;
     else cudaGetLastError();

@@ -265,9 +265,11 @@ def make_params(sample_rate, bins_per_tone, steps_per_symbol, max_candidates, mi
                              int(frame_hi), int(chunk_slots), int(flags))
 
 
-def alloc_slot_decodes(B: int, K: int, dev, zero: bool = True) -> SlotDecodes:
-    """Result arrays of a batch; zero=False leaves them uninitialised (for callers that overwrite every element)."""
-    mk = torch.zeros if zero else torch.empty
+def alloc_slot_decodes(B: int, K: int, dev, zero: bool = True, pin: bool = False) -> SlotDecodes:
+    """Result arrays of a batch; zero=False leaves them uninitialised (for callers that overwrite every element);
+    pin=True (host arrays only): page-locked memory from torch's caching host allocator."""
+    base = torch.zeros if zero else torch.empty
+    mk = (lambda *a, **k: base(*a, pin_memory=True, **k)) if pin else base
     i32, u8 = torch.int32, torch.uint8
     return SlotDecodes(
         cand_time=mk((B, K), dtype=i32, device=dev), cand_freq=mk((B, K), dtype=i32, device=dev),
@@ -311,7 +313,7 @@ class SlotDecoder:
         return o
 
 
-def decode_host_native(waves: torch.Tensor, params: _lib.DecodeParams, piece_slots: int = 128, device=None) -> SlotDecodes:
+def decode_host_native(waves: torch.Tensor, params: _lib.DecodeParams, piece_slots: int = 256, device=None) -> SlotDecodes:
     """Host [B, N] tensor -> HOST results through ft8b_decode_slots_host: the library's own C++ host path (two streams,
     double-buffered audio, pinned staging for pageable input).  No torch CUDA tensor is involved; torch only provides the
     host arrays here.  This is what decode_slots uses for host input."""
@@ -319,7 +321,9 @@ def decode_host_native(waves: torch.Tensor, params: _lib.DecodeParams, piece_slo
     assert not waves.is_cuda and waves.dim() == 2 and waves.stride(1) == 1
     B, N = waves.shape
     K = params.max_candidates
-    out = alloc_slot_decodes(B, K, torch.device("cpu"), zero=False)      # the library writes every element of all nine arrays
+    # the library writes every element of all nine arrays; large result sets go into page-locked arrays (cached by torch's
+    # host allocator), which the library fills by direct device-to-host copies
+    out = alloc_slot_decodes(B, K, torch.device("cpu"), zero=False, pin=B * K * 35 >= (1 << 20))
     if B:
         _lib.check(_lib.lib().ft8b_decode_slots_host(
             _p(waves), wave_dtype_code(waves), B, N, waves.stride(0), C.byref(params), dev.index if dev.index is not None else -1,
@@ -328,7 +332,7 @@ def decode_host_native(waves: torch.Tensor, params: _lib.DecodeParams, piece_slo
     return out
 
 
-def decode_host_batch(waves: torch.Tensor, params: _lib.DecodeParams, piece_slots: int = 128, device=None) -> SlotDecodes:
+def decode_host_batch(waves: torch.Tensor, params: _lib.DecodeParams, piece_slots: int = 256, device=None) -> SlotDecodes:
     """Host [B, N] tensor -> device results, with the H2D copy of piece i+1 overlapping the kernels of
     piece i (two device staging buffers, one copy stream).  Pinned host memory copies asynchronously."""
     dev = device or require_cuda()

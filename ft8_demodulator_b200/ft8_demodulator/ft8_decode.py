@@ -249,7 +249,7 @@ class BatchDecodes:
 
 def decode_slots(waves, sample_rate, bins_per_tone: int = 2, steps_per_symbol: int = 2, max_candidates: int = 20,
                  min_score=10, max_iterations: int = 20, freq_min=None, freq_max=None, time_min=None, time_max=None,
-                 chunk_slots: int = 0, return_device: bool = False, piece_slots: int = 128, pcm16: bool = False,
+                 chunk_slots: int = 0, return_device: bool = False, piece_slots: int = 256, pcm16: bool = False,
                  strict_topk: bool = False):
     """Decode a batch of equal-length slots: waves [B, N] (NumPy or torch, host or device, float32/float64).
 

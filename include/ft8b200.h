@@ -244,7 +244,7 @@ int ft8b_decode_slots(const void *wave, int wave_dtype, int64_t n_slots, int64_t
  * array library needed; this is what `e2e` in bench.py times).  wave and all nine result arrays are host pointers;
  * the library owns two streams, two device audio buffers, the chunk workspace and the device result arrays on
  * `device` (-1 = the calling thread's current device; cached between calls, grow-only, freed by ft8b_release).  The batch runs in pieces of `piece_slots`
- * slots (0 = 128): the host-to-device copy of piece i+1 overlaps the kernels of piece i.  Page-locked caller memory is
+ * slots (0 = 256): the host-to-device copy of piece i+1 overlaps the kernels of piece i.  Page-locked caller memory is
  * copied from directly; pageable memory is gathered into pinned staging buffers by persistent host threads first
  * (streaming stores; ft8b_set_host_staging).
  * The nine result arrays come back as ONE device-to-host copy into a pinned mirror and are then copied out on the host.
