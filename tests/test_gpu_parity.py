@@ -919,6 +919,32 @@ def test_host_abi_ragged_tail_with_small_chunks():
     assert np.array_equal(pl, r3.payload.numpy()) and np.array_equal(le, r3.ldpc_errors.numpy())
 
 
+def test_host_abi_direct_result_copies():
+    """Result sets of 1 MB and more go device-to-host straight into page-locked caller arrays (no mirror, no host
+    memcpy): 16 slots x K = 2000 through decode_slots (which then allocates pinned result arrays) and through the raw
+    entry point with pinned and with pageable NumPy-backed arrays - all equal to the device-resident run."""
+    import ctypes as C
+    from ft8_demodulator_b200 import _lib
+    kw = dict(bins_per_tone=2, steps_per_symbol=2, max_candidates=2000, min_score=3, max_iterations=5)
+    base = np.stack([synth.c3_slot(40 + i)[0] for i in range(4)]).astype(np.float32)
+    x = np.concatenate([base, base[::-1], base, base[::-1]])          # 16 slots
+    ref = fd.decode_slots(torch.from_numpy(x).cuda(), 12000, return_device=True, **kw)
+    got = fd.decode_slots(x, 12000, piece_slots=6, **kw)
+    assert got.arrays.ok.is_pinned() and _same_decodes(got.arrays, ref)
+    g = fd.decode_geometry(x.shape[1], 12000, 2, 2, None, None, None, None)
+    prm = engine.make_params(12000, 2, 2, 2000, 3, 5, g["bin_lo"], g["bin_hi"], g["frame_lo"], g["frame_hi"])
+    for pin in (True, False):
+        out = engine.alloc_slot_decodes(16, 2000, torch.device("cpu"), zero=False, pin=pin)
+        for f in out.__dataclass_fields__:
+            getattr(out, f).fill_(99)
+        p = lambda t: t.data_ptr()
+        rc = _lib.lib().ft8b_decode_slots_host(x.ctypes.data, _lib.DTYPE_F32, 16, x.shape[1], x.shape[1], C.byref(prm), -1, 5,
+                                               p(out.cand_time), p(out.cand_freq), p(out.cand_score), p(out.n_cand), p(out.ok),
+                                               p(out.ldpc_errors), p(out.crc_extracted), p(out.crc_calculated), p(out.payload))
+        assert rc == 0, _lib.lib().ft8b_last_error()
+        assert _same_decodes(out, ref), pin
+
+
 def test_empty_search_defines_every_output():
     """'Nothing to search' (K = 0 is separate; here a band of 10 bins: fewer than 7 tones wide) returns zeros in all nine
     output arrays of ft8b_decode_slots, not whatever the caller's buffers held."""
