@@ -351,7 +351,7 @@ int host_call(HostPath &h, const HostCall &c) {
         int64_t left = n_slots;
         while (left > piece) { sizes.push_back(piece); left -= piece; }
         if (n_slots > 2 * piece) {
-            while (left > 32) { const int64_t h = (left + 1) / 2; sizes.push_back(h); left -= h; }
+            while (left > 32) { const int64_t half = (left + 1) / 2; sizes.push_back(half); left -= half; }
         }
         if (left > 0) sizes.push_back(left);
     }
