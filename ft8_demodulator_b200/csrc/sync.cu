@@ -366,6 +366,69 @@ __device__ __forceinline__ bool sel_better(double sa, long long ia, double sb, l
     return (sa > sb) || (sa == sb && ia < ib);
 }
 
+// Bitonic sort of the candidate list over Kpad entries.  BY_INDEX = false: (score descending, tag ascending) - the
+// order of the result; BY_INDEX = true: tag ascending only (scan order = the order the reference pushed them in).
+template <int THREADS, bool BY_INDEX>
+__device__ __forceinline__ void sel_bitonic(double *hs, long long *hi, int Kpad, int tid) {
+    for (int size = 2; size <= Kpad; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = tid; i < Kpad; i += THREADS) {
+                const int j = i ^ stride;
+                if (j > i) {
+                    const bool up = ((i & size) == 0);   // "up" = better elements first
+                    const double si = hs[i], sj = hs[j];
+                    const long long ii = hi[i], ij = hi[j];
+                    const bool j_better = BY_INDEX ? (ij < ii) : sel_better(sj, ij, si, ii);
+                    if (up ? j_better : !j_better) { hs[i] = sj; hs[j] = si; hi[i] = ij; hi[j] = ii; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// Exact score ties inside the list (two candidates whose only in-range Costas blocks are the same cells - it happens
+// with time-cropped or short spectrograms - or digital silence).  The reference sorts its heap ARRAY with a stable
+// key sort (ft8_decode.py:140), so tied candidates come out in heap-array order, and a tie that heapq itself compares
+// raises (the tuple comparison falls through to FT8Candidate).  This replays CPython's heapq on the list: hs / hi hold
+// the first n passers in push (scan) order on entry and the heap array on exit.  `replace`: a later record evicts the
+// root (ft8_decode.py:136-137) - the sift path of heapreplace only has to be checked for compared ties, the
+// arrangement below the root is unchanged because the new key is strictly the smallest.  Returns false when the
+// reference would have raised (a compared tie); the arrays are then some permutation of the input.
+__device__ bool sel_heap_replay(double *hs, long long *hi, int n, bool replace, double rec_s, long long rec_i) {
+    for (int m = 1; m < n; ++m) {                           // heappush: heapq._siftdown(heap, 0, m)
+        const double s = hs[m];
+        const long long id = hi[m];
+        int pos = m;
+        bool tie = false;
+        while (pos > 0) {
+            const int parent = (pos - 1) >> 1;
+            const double ps = hs[parent];
+            if (s == ps) { tie = true; break; }             // equal keys: the tuple comparison reaches the candidates
+            if (!(s > ps)) break;                           // newitem < parent  <=>  -s < -ps
+            hs[pos] = ps; hi[pos] = hi[parent];
+            pos = parent;
+        }
+        hs[pos] = s; hi[pos] = id;
+        if (tie) return false;
+    }
+    if (replace) {                                          // heapreplace: heapq._siftup(heap, 0) walks the smaller-key children
+        int child = 1;
+        while (child < n) {
+            const int right = child + 1;
+            if (right < n) {
+                if (hs[child] == hs[right]) return false;
+                if (!(hs[child] > hs[right])) child = right;
+            }
+            child = 2 * child + 1;
+        }
+        hs[0] = rec_s; hi[0] = rec_i;
+    }
+    return true;
+}
+constexpr int kSelTagShift = 40;                            // hi = (heap position << 40) | scan index in the tie path
+constexpr long long kSelIdxMask = (1LL << kSelTagShift) - 1;
+
 // THREADS: 256 for short lists (K <= 64: four CTAs per SM hide each other's barrier and DRAM latencies - 0.235 ms per
 // 4096 slots at K = 20 against 0.47 ms with one 1024-thread CTA per SM), 1024 for long ones (the sort and the
 // compaction of thousands of candidates want the threads).
@@ -383,6 +446,9 @@ __global__ void __launch_bounds__(THREADS) select_candidates_kernel(const SelArg
     __shared__ long long red_c[32];
     __shared__ double s_rec_s;          // the later record (phase B): score and scan index
     __shared__ long long s_rec_i;
+    __shared__ double s_ev_s;           // the element the record evicted in B3 (needed again if the list holds exact ties)
+    __shared__ long long s_ev_i;
+    __shared__ int s_replaced;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int64_t slot = blockIdx.x;
     const double *sc = a.scores + slot * a.L;
@@ -390,7 +456,7 @@ __global__ void __launch_bounds__(THREADS) select_candidates_kernel(const SelArg
     const int K = a.K;
 
     for (int i = tid; i < a.Kpad; i += kSelThreads) { hs[i] = -INFINITY; hi[i] = 0x7fffffffffffffffLL; }
-    if (tid == 0) { s_base = 0; s_done = 0; s_cut = -1; }
+    if (tid == 0) { s_base = 0; s_done = 0; s_cut = -1; s_replaced = 0; }
     __syncthreads();
 
     // ---- phase A: first K passers in scan order (ordered compaction) ----
@@ -565,31 +631,42 @@ __global__ void __launch_bounds__(THREADS) select_candidates_kernel(const SelArg
         int best = 0;
         for (int i = 1; i < n_first; ++i)
             if (sel_better(hs[i], hi[i], hs[best], hi[best])) best = i;
-        if (s_rec_s > hs[best]) { hs[best] = s_rec_s; hi[best] = s_rec_i; }
+        if (s_rec_s > hs[best]) { s_ev_s = hs[best]; s_ev_i = hi[best]; s_replaced = 1; hs[best] = s_rec_s; hi[best] = s_rec_i; }
     }
     __syncthreads();
 
     // ---- phase C: sort H by (score desc, scan index asc) - bitonic over Kpad ----
-    for (int size = 2; size <= a.Kpad; size <<= 1) {
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            for (int i = tid; i < a.Kpad; i += kSelThreads) {
-                const int j = i ^ stride;
-                if (j > i) {
-                    const bool up = ((i & size) == 0);   // "up" = better elements first
-                    const double si = hs[i], sj = hs[j];
-                    const long long ii = hi[i], ij = hi[j];
-                    const bool j_better = sel_better(sj, ij, si, ii);
-                    if (up ? j_better : !j_better) { hs[i] = sj; hs[j] = si; hi[i] = ij; hi[j] = ii; }
-                }
+    sel_bitonic<THREADS, false>(hs, hi, a.Kpad, tid);
+    // ---- phase D (rare): exact ties in the list come out in the reference's heap-array order ----
+    int tie = 0;
+    for (int i = tid; i + 1 < n_first; i += kSelThreads) tie |= (hs[i] == hs[i + 1]) ? 1 : 0;
+    if (__syncthreads_or(tie)) {
+        const bool replaced = s_replaced != 0;
+        if (replaced)                                       // back to the K elements that were pushed
+            for (int i = tid; i < n_first; i += kSelThreads)
+                if (hi[i] == s_rec_i) { hs[i] = s_ev_s; hi[i] = s_ev_i; }
+        __syncthreads();
+        sel_bitonic<THREADS, true>(hs, hi, a.Kpad, tid);    // push order
+        if (tid == 0) {
+            if (sel_heap_replay(hs, hi, n_first, replaced, s_rec_s, s_rec_i)) {
+                for (int i = 0; i < n_first; ++i) hi[i] |= (long long)i << kSelTagShift;
+            } else if (replaced) {
+                // the reference raises here; what is returned instead is the scan-order list of B3
+                int best = 0;
+                for (int i = 1; i < n_first; ++i)
+                    if (sel_better(hs[i], hi[i], hs[best], hi[best])) best = i;
+                hs[best] = s_rec_s; hi[best] = s_rec_i;
             }
-            __syncthreads();
         }
+        __syncthreads();
+        sel_bitonic<THREADS, false>(hs, hi, a.Kpad, tid);
     }
     for (int i = tid; i < K; i += kSelThreads) {
         const int64_t o = slot * K + i;
         if (i < n_first) {
-            a.cand_time[o] = a.t0 + (int)(hi[i] / a.nf);
-            a.cand_freq[o] = (int)(hi[i] % a.nf);
+            const long long idx = hi[i] & kSelIdxMask;
+            a.cand_time[o] = a.t0 + (int)(idx / a.nf);
+            a.cand_freq[o] = (int)(idx % a.nf);
             a.cand_score[o] = hs[i];
         } else {
             a.cand_time[o] = 0; a.cand_freq[o] = 0; a.cand_score[o] = 0.0;

@@ -285,7 +285,31 @@ def case_c4():
     save("c4.npz", **arrays)
 
 
-CASES = dict(c4=case_c4, kat=case_kat, c1=case_c1, bp=case_bp, wav=case_wav, c2=case_c2, rates=case_rates)
+def case_ties():
+    """Exact score ties inside the candidate list (C1 slot, time-cropped spectrogram: candidates 36 symbols apart whose
+    only in-range Costas blocks are the same cells).  The reference returns tied candidates in heap-array order
+    (stable key sort of the heap, ft8_decode.py:140); K = 30 adds the record replacement on top."""
+    slot = synth.c1_slot()
+    arrays = dict(slot_sha256=np.array(sha(slot.astype(np.float32))))
+    base = dict(max_iterations=5, freq_min=300.0, freq_max=900.0, time_min=0.56, time_max=14.84)
+    for tag, kw in (("k150_s4", dict(max_candidates=150, min_score=4, **base)),     # fewer passers than K
+                    ("k38_s4", dict(max_candidates=38, min_score=4, **base)),       # full heap, later passers
+                    ("k12_s5", dict(max_candidates=12, min_score=5, **base))):      # heapq compares a tie: TypeError
+        arrays[tag + "__kw"] = np.array(json.dumps(kw))
+        try:
+            d = traced_decode(slot, 12000, llr_keep=2, bins_per_tone=2, steps_per_symbol=2, **kw)
+        except TypeError as e:
+            arrays[tag + "__raises"] = np.array("TypeError")
+            print("   ties %s: the reference raises TypeError (%s)" % (tag, str(e)[:60]))
+            continue
+        sc = d["cand_score"]
+        n_ties = int(np.sum(sc[1:] == sc[:-1]))
+        arrays.update(prefixed(tag + "__", d))
+        print("   ties %s: %d cands, %d adjacent exact ties, %d decodes" % (tag, len(sc), n_ties, len(d["res_hash"])))
+    save("ties.npz", **arrays)
+
+
+CASES = dict(ties=case_ties, c4=case_c4, kat=case_kat, c1=case_c1, bp=case_bp, wav=case_wav, c2=case_c2, rates=case_rates)
 
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)

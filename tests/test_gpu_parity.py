@@ -422,6 +422,65 @@ def test_c2_golden(tag, kw):
         assert decoded == set(bytes(p) for p in gold["res_payload"]) and len(decoded & set(payloads)) >= 20
 
 
+@pytest.mark.parametrize("tag", ["k150_s4", "k38_s4"])
+def test_exact_score_ties_golden(c1_slot, tag):
+    """Exact score ties inside the list (time-cropped spectrogram): the reference's heap-array order, not scan order."""
+    g = load_golden("ties.npz")
+    kw = json.loads(str(g[tag + "__kw"]))
+    gold = golden_case(g, tag)
+    assert int(np.sum(gold["cand_score"][1:] == gold["cand_score"][:-1])) >= 3
+    batch = fd.decode_slots(c1_slot.astype(np.float32).reshape(1, -1), 12000, 2, 2, **kw)
+    check_against_gold(batch.arrays, gold)
+    check_result_list(fd.decode_ft8_message(c1_slot, 12000, 2, 2, **kw), gold)
+
+
+def test_select_ties_vs_heapq():
+    """Score maps with many exact ties (quantised scores) through the stand-alone selection: wherever the reference's
+    heapq does not compare a tie, the list equals what Python's own heapq gives (heap_reference_list) - K below, at and above the number of passers."""
+    rng = np.random.default_rng(21)
+    nt, nf, t0 = 12, 40, -4
+    checked = raised = 0
+    for trial in range(60):
+        levels = int(rng.choice([3, 6, 12, 40]))
+        smap = rng.integers(0, levels, (nt, nf)).astype(np.float64) + (rng.random((nt, nf)) < 0.5) * rng.random((nt, nf))
+        K = int(rng.choice([1, 2, 5, 17, 64, 65, 200, 600]))
+        thr = float(rng.choice([0.0, 1.0, levels / 2]))
+        want = heap_reference_list(smap, t0, K, thr)
+        ct, cf, cs, n, _ = engine.select_candidates(engine._dev(smap.reshape(1, nt, nf)), t0, K, thr)
+        n = int(n[0])
+        got = list(zip(ct[0, :n].tolist(), cf[0, :n].tolist(), cs[0, :n].tolist()))
+        if want is None:
+            raised += 1                      # the reference raises TypeError: only the multiset is defined
+            continue
+        checked += 1
+        assert got == want, (trial, K, thr)
+    assert checked >= 10 and raised >= 5
+
+
+def heap_reference_list(smap, t0, K, thr):
+    """ft8_decode.py:124-140 on a given score map with Python's own heapq: (abs_time, abs_freq, score) in the
+    reference's order, or None where the reference raises (two equal scores compared inside heapq)."""
+    import heapq
+
+    class Cand:                              # like FT8Candidate: no ordering defined
+        def __init__(self, t, f):
+            self.t, self.f = t, f
+    heap = []
+    try:
+        for ti in range(smap.shape[0]):
+            for f in range(smap.shape[1]):
+                score = float(smap[ti, f])
+                if score == float("-inf") or score < thr:
+                    continue
+                if len(heap) < K:
+                    heapq.heappush(heap, (-score, Cand(t0 + ti, f)))
+                elif -score < heap[0][0]:
+                    heapq.heapreplace(heap, (-score, Cand(t0 + ti, f)))
+    except TypeError:
+        return None
+    return [(c.t, c.f, -k) for k, c in sorted(heap, key=lambda x: x[0])]
+
+
 @pytest.mark.parametrize("tag", ["fs6000", "fs10000_osr4", "fs3500", "fs12000_osr10", "fs32768"])
 def test_other_rates_golden(tag):
     g = load_golden("rates.npz")

@@ -99,6 +99,28 @@ def test_c1_decode(orc, c1_slot, tag, kw):
         assert recs[0]["payload"] == synth.C1_PAYLOAD and recs[0]["crc_calculated"] == 7997
 
 
+@pytest.mark.parametrize("tag", ["k150_s4", "k38_s4", "k12_s5"])
+def test_exact_score_ties(orc, c1_slot, tag):
+    """Tied candidates come out in the reference's heap-array order (stable key sort, ft8_decode.py:140); a tie that
+    heapq itself compares raises TypeError in the reference and in the oracle."""
+    g = load_golden("ties.npz")
+    kw = json.loads(str(g[tag + "__kw"]))
+    if tag + "__raises" in g.files:
+        with pytest.raises(TypeError):
+            orc.decode_all_candidates(c1_slot, 12000, 2, 2, kw["max_candidates"], kw["min_score"], kw["max_iterations"],
+                                      freq_min=kw["freq_min"], freq_max=kw["freq_max"], time_min=kw["time_min"], time_max=kw["time_max"])
+        return
+    gold = golden_case(g, tag)
+    sc = gold["cand_score"]
+    tied = np.flatnonzero(sc[1:] == sc[:-1])
+    assert len(tied) >= 3
+    # ... and the reference's order among them is NOT simply scan order (what a plain sort by (score, position) would give)
+    scan = [(int(gold["cand_time"][i]), int(gold["cand_freq"][i])) for i in range(len(sc))]
+    if tag == "k150_s4":
+        assert any(scan[i] > scan[i + 1] for i in tied)
+    check_traced(orc, c1_slot, 12000, gold, bins_per_tone=2, steps_per_symbol=2, **kw)
+
+
 def test_wav_fixture(orc):
     g = load_golden("wav_fs20k.npz")
     x = (g["samples_int16"].astype(np.float32) / 32767).astype(np.float64)

@@ -1,0 +1,129 @@
+"""Randomised differential test of the whole decode path on the GPU box (test infrastructure, not product):
+   python tools/fuzz_parity.py [trials] [seed]
+Every trial draws a geometry (sample rate, bins_per_tone, steps_per_symbol, slot length), decode parameters
+(max_candidates, min_score, max_iterations, band / time masks, chunking) and a small batch of slots (noise plus a
+few FT8 bursts, some silent or constant slots), decodes the batch through decode_slots (C ABI, CUDA) and compares
+every candidate record with the CPU oracle slot by slot: indices, flags, error counts, CRC fields and payloads
+exactly, scores to 1e-9 (tests/test_gpu_parity.py states the same bars).  Prints one JSON line."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "oracle")):
+    sys.path.insert(0, p)
+
+import ft8_oracle as orc  # noqa: E402
+from ft8_demodulator_b200 import synth  # noqa: E402
+from ft8_demodulator_b200.ft8_demodulator import ft8_decode as fd  # noqa: E402
+
+RATES = [12000, 12000, 12000, 6000, 8000, 10000, 3500, 4500, 16000, 20000, 24000]
+
+
+def draw_trial(rng):
+    fs = int(rng.choice(RATES))
+    b = int(rng.choice([1, 2, 2, 2, 3, 4]))
+    s = int(rng.choice([1, 2, 2, 2, 3, 4, 5]))
+    dur = float(rng.choice([13.0, 14.0, 15.0, 15.0, 15.0, 16.5]))
+    n = int(fs * dur) + int(rng.integers(0, 7))
+    B = int(rng.integers(1, 6))
+    kw = dict(max_candidates=int(rng.choice([1, 2, 5, 20, 20, 64, 65, 150])),
+              min_score=float(rng.choice([-3.0, 0.0, 1.0, 1.0, 2.5, 6.0, 10.0])),
+              max_iterations=int(rng.choice([0, 1, 5, 20, 20, 40])))
+    masks = {}
+    if rng.random() < 0.35:
+        masks["freq_min"] = float(rng.uniform(0, 400))
+    if rng.random() < 0.35:
+        masks["freq_max"] = float(rng.uniform(1200, min(3100, fs / 2 - 10)))
+    if rng.random() < 0.2:
+        masks["time_min"] = float(rng.uniform(0, 0.8))
+    if rng.random() < 0.2:
+        masks["time_max"] = float(rng.uniform(dur - 1.0, dur))
+    waves = np.zeros((B, n), dtype=np.float64)
+    for i in range(B):
+        kind = rng.random()
+        if kind < 0.08:
+            continue                                            # digital silence
+        if kind < 0.14:
+            waves[i] = float(rng.uniform(-1, 1))                # constant
+            continue
+        sig = np.zeros(n)
+        for _ in range(int(rng.integers(0, 4))):
+            payload = bytes(rng.integers(0, 256, 10, dtype=np.uint8))
+            payload = payload[:9] + bytes([payload[9] & 0xF8])
+            f0 = float(rng.uniform(150, min(2600, fs / 2 - 200)))
+            burst = synth.ft8_generator(payload, fs, f0) * 10 ** (float(rng.uniform(-18, 3)) / 20)
+            start = int(rng.uniform(0, max(1.0, dur - 12.7)) * fs)
+            m = min(len(burst), n - start)
+            if m > 0:
+                sig[start:start + m] += burst[:m]
+        waves[i] = sig + rng.standard_normal(n) * float(rng.choice([0.0, 0.3, 1.0, 1.0]))
+    waves = waves.astype(np.float32)
+    chunk = int(rng.choice([0, 0, 1, 2, 3]))
+    return fs, b, s, waves, kw, masks, chunk
+
+
+def compare(batch, ref_lists):
+    a = batch.arrays
+    for i, ref in enumerate(ref_lists):
+        if ref is None:
+            continue
+        if int(a.n_cand[i]) != len(ref):
+            return "slot %d: n_cand %d vs %d" % (i, int(a.n_cand[i]), len(ref))
+        for c, r in enumerate(ref):
+            got = (int(a.cand_time[i, c]), int(a.cand_freq[i, c]), bool(a.ok[i, c]), int(a.ldpc_errors[i, c]),
+                   int(a.crc_extracted[i, c]), int(a.crc_calculated[i, c]), bytes(a.payload[i, c].numpy()))
+            want = (r["abs_time"], r["abs_freq"], r["ok"], r["ldpc_errors"], r["crc_extracted"], r["crc_calculated"], r["payload"])
+            if got != want:
+                return "slot %d cand %d: %r vs %r" % (i, c, got, want)
+            if not abs(float(a.cand_score[i, c]) - r["score"]) < 1e-9:
+                return "slot %d cand %d: score %r vs %r" % (i, c, float(a.cand_score[i, c]), r["score"])
+    return None
+
+
+def main():
+    trials = int(sys.argv[1]) if len(sys.argv) > 1 else 60
+    seed = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+    rng = np.random.default_rng(seed)
+    failures, skipped, records, decoded = [], 0, 0, 0
+    t0 = time.time()
+    for t in range(trials):
+        fs, b, s, waves, kw, masks, chunk = draw_trial(rng)
+        desc = dict(trial=t, fs=fs, b=b, s=s, shape=list(waves.shape), chunk=chunk, **kw, **masks)
+        ref, short = [], False
+        for w in waves:
+            try:
+                ref.append(orc.decode_all_candidates(w.astype(np.float64), fs, b, s, kw["max_candidates"], kw["min_score"],
+                                                     kw["max_iterations"], **masks))
+            except TypeError:
+                ref.append(None)                                # exact score tie: the reference itself raises; slot not compared
+                skipped += 1
+            except IndexError:
+                short = True
+        if short:
+            ref = None
+        try:
+            batch = fd.decode_slots(waves, fs, b, s, chunk_slots=chunk, **kw, **masks)
+        except NotImplementedError as e:
+            skipped += 1
+            desc["unsupported"] = str(e)[:80]
+            continue
+        if ref is None:
+            if len(batch.to_lists()) and any(batch.to_lists()):
+                failures.append(dict(desc, why="reference: input shorter than a window; GPU returned decodes"))
+            continue
+        why = compare(batch, ref)
+        records += sum(len(r) for r in ref if r is not None)
+        decoded += sum(1 for r in ref if r is not None for c in r if c["ok"])
+        if why:
+            failures.append(dict(desc, why=why))
+    print(json.dumps(dict(tool="fuzz_parity", trials=trials, seed=seed, skipped=skipped, candidate_records_compared=records,
+                          decodes_among_them=decoded, failures=failures, seconds=round(time.time() - t0, 1))))
+    sys.exit(1 if failures else 0)
+
+
+if __name__ == "__main__":
+    main()
