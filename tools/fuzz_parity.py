@@ -20,14 +20,14 @@ import ft8_oracle as orc  # noqa: E402
 from ft8_demodulator_b200 import synth  # noqa: E402
 from ft8_demodulator_b200.ft8_demodulator import ft8_decode as fd  # noqa: E402
 
-RATES = [12000, 12000, 12000, 6000, 8000, 10000, 3500, 4500, 16000, 20000, 24000]
+RATES = [12000, 12000, 12000, 6000, 8000, 10000, 3500, 4500, 16000, 20000, 24000, 11025, 22050, 44100, 48000, 7350]
 
 
 def draw_trial(rng):
     fs = int(rng.choice(RATES))
     b = int(rng.choice([1, 2, 2, 2, 3, 4]))
     s = int(rng.choice([1, 2, 2, 2, 3, 4, 5]))
-    dur = float(rng.choice([13.0, 14.0, 15.0, 15.0, 15.0, 16.5]))
+    dur = float(rng.choice([10.0, 12.7, 13.0, 14.0, 15.0, 15.0, 15.0, 16.5]))
     n = int(fs * dur) + int(rng.integers(0, 7))
     B = int(rng.integers(1, 6))
     kw = dict(max_candidates=int(rng.choice([1, 2, 5, 20, 20, 64, 65, 150])),
@@ -61,9 +61,29 @@ def draw_trial(rng):
             if m > 0:
                 sig[start:start + m] += burst[:m]
         waves[i] = sig + rng.standard_normal(n) * float(rng.choice([0.0, 0.3, 1.0, 1.0]))
-    waves = waves.astype(np.float32)
     chunk = int(rng.choice([0, 0, 1, 2, 3]))
-    return fs, b, s, waves, kw, masks, chunk
+    # input type and placement: what the GPU gets (`given`) and the float64 values it stands for (`waves`, the oracle's input)
+    kind = str(rng.choice(["f32", "f32", "f64", "pcm16", "f32_pinned", "f32_device", "f64_device"]))
+    extra = {}
+    if kind == "pcm16":
+        pcm = np.clip(np.round(waves / max(1e-9, np.abs(waves).max()) * 20000.0), -32768, 32767).astype(np.int16)
+        given = pcm
+        waves = (pcm.astype(np.float32) / np.float32(32767)).astype(np.float64)        # from_wave.py:62-66
+        extra["pcm16"] = True
+    elif kind.startswith("f64"):
+        given = waves
+    else:
+        given = waves.astype(np.float32)
+        waves = given.astype(np.float64)
+    if kind.endswith("_pinned"):
+        import torch
+        given = torch.from_numpy(given).pin_memory()
+    elif kind.endswith("_device"):
+        import torch
+        given = torch.from_numpy(given).cuda()
+    if rng.random() < 0.3:
+        extra["piece_slots"] = int(rng.choice([1, 2, 3]))
+    return fs, b, s, waves, kw, masks, chunk, given, kind, extra
 
 
 def compare(batch, ref_lists):
@@ -91,12 +111,12 @@ def main():
     failures, skipped, records, decoded = [], 0, 0, 0
     t0 = time.time()
     for t in range(trials):
-        fs, b, s, waves, kw, masks, chunk = draw_trial(rng)
-        desc = dict(trial=t, fs=fs, b=b, s=s, shape=list(waves.shape), chunk=chunk, **kw, **masks)
+        fs, b, s, waves, kw, masks, chunk, given, kind, extra = draw_trial(rng)
+        desc = dict(trial=t, fs=fs, b=b, s=s, shape=list(waves.shape), chunk=chunk, input=kind, **kw, **masks, **extra)
         ref, short = [], False
         for w in waves:
             try:
-                ref.append(orc.decode_all_candidates(w.astype(np.float64), fs, b, s, kw["max_candidates"], kw["min_score"],
+                ref.append(orc.decode_all_candidates(w, fs, b, s, kw["max_candidates"], kw["min_score"],
                                                      kw["max_iterations"], **masks))
             except TypeError:
                 ref.append(None)                                # exact score tie: the reference itself raises; slot not compared
@@ -106,7 +126,7 @@ def main():
         if short:
             ref = None
         try:
-            batch = fd.decode_slots(waves, fs, b, s, chunk_slots=chunk, **kw, **masks)
+            batch = fd.decode_slots(given, fs, b, s, chunk_slots=chunk, **kw, **masks, **extra)
         except NotImplementedError as e:
             skipped += 1
             desc["unsupported"] = str(e)[:80]
