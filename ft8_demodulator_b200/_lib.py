@@ -45,6 +45,7 @@ SIGNATURES = {
     "ft8b_sync_scores": (_i, [_vp, _i64, _i, _i, _i, _i, _vp, _vp]),
     "ft8b_select_candidates": (_i, [_vp, _i64, _i, _i, _i, _i, _d, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ft8b_find_candidates": (_i, [_vp, _vp, _i64, _i, _i, _i, _i, _i, _d, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ft8b_sync_score_at": (_i, [_vp, _i64, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
     "ft8b_select_topk": (_i, [_vp, _i64, _i, _i, _i, _i, _d, _vp, _vp, _vp, _vp, _vp]),
     "ft8b_decode_candidates": (_i, [_vp, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                     _vp]),

@@ -23,6 +23,7 @@ int stft_db(const void *, int, int64_t, int64_t, int64_t, int, int, int, int, in
 int release_plans();
 int sync_tiles_per_slot(int, int, int, int);
 int sync_scores(const double *, int64_t, int, int, int, int, double *, SyncTile *, cudaStream_t);
+int sync_score_at(const double *, int64_t, int, int, int, int, const int32_t *, const int32_t *, int, double *, cudaStream_t);
 int select_candidates(const double *, int64_t, int, int, int, int, double, int32_t *, int32_t *, double *, int32_t *,
                       int32_t *, const SyncTile *, int, const double *, int, int, int, int, cudaStream_t);
 int decode_candidates(const double *, int64_t, int, int, int, int, const int32_t *, const int32_t *, const int32_t *, int,
@@ -199,6 +200,11 @@ int ft8b_find_candidates(const double *mag, const double *scores, int64_t n_slot
     ft8b_search_ranges(T, F, s, b, &t0, &nt, &nf);
     return select_candidates(scores, n_slots, nt, nf, t0, K, min_score, cand_time, cand_freq, cand_score, n_cand, n_pass,
                              nullptr, 0, mag, T, F, s, b, (cudaStream_t)stream);
+}
+
+int ft8b_sync_score_at(const double *mag, int64_t n_slots, int T, int F, int s, int b, const int32_t *cand_time,
+                       const int32_t *cand_freq, int n_per_slot, double *score, void *stream) {
+    return sync_score_at(mag, n_slots, T, F, s, b, cand_time, cand_freq, n_per_slot, score, (cudaStream_t)stream);
 }
 
 int ft8b_select_topk(const double *scores, int64_t n_slots, int nt, int nf, int t0, int K, double min_score,

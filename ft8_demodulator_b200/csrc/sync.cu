@@ -922,6 +922,28 @@ int sync_scores(const double *mag, int64_t n_slots, int T, int F, int s, int b, 
     return 0;
 }
 
+// ft8_sync_score at given positions, one thread per score, the reference's own running sum (ref_sync_score above)
+__global__ void sync_score_at_kernel(const double *mag, int64_t n_slots, int T, int F, int s, int b, const int32_t *ct,
+                                     const int32_t *cf, int n_per_slot, double *out) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n_slots * n_per_slot) return;
+    const int64_t slot = i / n_per_slot;
+    const int at = ct[i], af = cf[i];
+    if (af < 0 || af + 7 * b >= F) { out[i] = nan(""); return; }
+    out[i] = ref_sync_score(mag + slot * (int64_t)T * F, F, s, b, T / s, at, af);
+}
+
+int sync_score_at(const double *mag, int64_t n_slots, int T, int F, int s, int b, const int32_t *ct, const int32_t *cf,
+                  int n_per_slot, double *score, cudaStream_t stream) {
+    if (!mag || !ct || !cf || !score) FT8B_ARG_FAIL("ft8b_sync_score_at: null pointer");
+    if (T < 0 || F < 0 || s < 1 || b < 1 || n_per_slot < 0 || n_slots < 0) FT8B_ARG_FAIL("ft8b_sync_score_at: bad shape");
+    const int64_t n = n_slots * n_per_slot;
+    if (n == 0) return 0;
+    sync_score_at_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(mag, n_slots, T, F, s, b, ct, cf, n_per_slot, score);
+    FT8B_LAUNCH_CHECK("sync_score_at_kernel");
+    return 0;
+}
+
 int select_candidates(const double *scores, int64_t n_slots, int nt, int nf, int t0, int K, double min_score,
                       int32_t *cand_time, int32_t *cand_freq, double *cand_score, int32_t *n_cand, int32_t *n_pass,
                       const SyncTile *tiles, int n_tiles, const double *mag, int T, int F, int s, int b,

@@ -79,6 +79,21 @@ def sync_scores(mag: torch.Tensor, time_osr: int, freq_osr: int):
     return scores, t0
 
 
+def sync_score_at(mag: torch.Tensor, time_osr: int, freq_osr: int, cand_time: torch.Tensor, cand_freq: torch.Tensor):
+    """ft8_sync_score at given positions: mag [B, T, F], cand_time / cand_freq i32 [B, n] -> scores f64 [B, n], each the
+    reference's own running sum (bit-equal on the same spectrogram; ft8b_sync_score_at)."""
+    assert mag.is_cuda and mag.dtype == _F64 and mag.is_contiguous() and mag.dim() == 3
+    B, T, F = mag.shape
+    assert cand_time.shape == cand_freq.shape and cand_time.shape[0] == B and cand_time.dtype == cand_freq.dtype == torch.int32
+    assert cand_time.is_contiguous() and cand_freq.is_contiguous()
+    n = cand_time.shape[1]
+    out = torch.empty((B, n), dtype=_F64, device=mag.device)
+    if B and n:
+        _lib.check(_lib.lib().ft8b_sync_score_at(_p(mag), B, T, F, time_osr, freq_osr, _p(cand_time), _p(cand_freq), n,
+                                                 _p(out), _stream()), "ft8b_sync_score_at")
+    return out
+
+
 def select_candidates(scores: torch.Tensor, t0: int, K: int, min_score: float, strict_topk: bool = False,
                       mag: torch.Tensor = None, time_osr: int = 0, freq_osr: int = 0):
     """S2b.  scores [B, nt, nf] -> (cand_time i32 [B,K], cand_freq i32 [B,K], cand_score f64 [B,K], n_cand i32 [B],

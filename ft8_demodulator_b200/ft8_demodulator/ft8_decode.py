@@ -66,18 +66,13 @@ def _score_map(wf: FT8Waterfall):
 # ft8_decode.py:47-149
 # ------------------------------------------------------------------------------------------------
 def ft8_sync_score(wf: FT8Waterfall, candidate: FT8Candidate) -> float:
-    """Costas sync score of one candidate (ft8_decode.py:47-100).  The whole score map of the waterfall
-    is computed on the GPU on first use and cached; positions outside ft8_find_candidates' search
-    range are not covered."""
-    scores, t0, host = _score_map(wf)
-    if host is None:
-        host = scores[0].cpu().numpy()
-        wf.__dict__["_b200_scores"] = (scores, t0, host)
-    ti = candidate.abs_time - t0
-    if not (0 <= ti < host.shape[0] and 0 <= candidate.abs_freq < host.shape[1]):
-        raise IndexError("candidate (%d, %d) is outside the candidate search range" % (candidate.abs_time,
-                                                                                     candidate.abs_freq))
-    return float(host[ti, candidate.abs_freq])
+    """Costas sync score of one candidate (ft8_decode.py:47-100), evaluated on the GPU exactly as the reference does
+    (one running sum, one division: ft8b_sync_score_at) - bit-equal on the same waterfall, at any abs_time.  A
+    frequency whose eight tone bins do not fit the waterfall raises IndexError, as the reference's indexing does."""
+    _check_candidate(wf, candidate)
+    mag = _device_waterfall(wf)
+    ct, cf, _ = _cand_tensors(candidate, mag.device)
+    return float(engine.sync_score_at(mag, wf.time_osr, wf.freq_osr, ct, cf).cpu()[0, 0])
 
 
 def ft8_find_candidates(wf: FT8Waterfall, num_candidates: int, min_score: int, strict_topk: bool = False) -> List[FT8Candidate]:

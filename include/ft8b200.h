@@ -95,7 +95,9 @@ int ft8b_sync_scores(const double *mag, int64_t n_slots, int T, int F, int time_
  * S2b Candidate selection with the reference's exact heap semantics (ft8_decode.py:127-140):
  *     the first K threshold passers in scan order, the running best replaced by every later
  *     strictly greater score, result sorted by descending score.  K <= FT8B_MAX_CANDIDATES.
- *     Exact score ties (the reference raises TypeError) are ordered by scan position.
+ *     Exact score ties: where the reference returns a list, tied candidates come out in its heap-array order (CPython's
+ *     heapq replayed on the list; the reference sorts the heap with a stable key sort, :140); where its heapq compares
+ *     two equal scores (the reference raises TypeError) they are ordered by scan position.
  *     n_pass (optional, may be NULL) receives the number of threshold passers per slot.
  */
 int ft8b_select_candidates(const double *scores, int64_t n_slots, int nt, int nf, int t0, int K, double min_score,
@@ -115,6 +117,15 @@ int ft8b_select_candidates(const double *scores, int64_t n_slots, int nt, int nf
 int ft8b_find_candidates(const double *mag, const double *scores, int64_t n_slots, int T, int F, int time_osr, int freq_osr,
                          int K, double min_score, int32_t *cand_time, int32_t *cand_freq, double *cand_score,
                          int32_t *n_cand, int32_t *n_pass, void *stream);
+/*
+ * ft8_sync_score (ft8_decode.py:47-100) for given candidates, evaluated exactly as the reference does (one running sum
+ * in (m, k, lower/higher/earlier/later) order, one IEEE division; -inf when nothing is compared or the sum is not
+ * finite): score[slot][i] for (cand_time, cand_freq)[slot][i], i < n_per_slot.  Any abs_time; 0 <= abs_freq and
+ * abs_freq + 7*freq_osr < F is the caller's to guarantee (the reference indexes out of range there), violating
+ * candidates get NaN.  Bit-equal to the reference on the same spectrogram.
+ */
+int ft8b_sync_score_at(const double *mag, int64_t n_slots, int T, int F, int time_osr, int freq_osr,
+                       const int32_t *cand_time, const int32_t *cand_freq, int n_per_slot, double *score, void *stream);
 /*
  * OPT-IN EXTENSION (not the reference's behaviour; SURVEY Appendix D "may add an opt-in strict top-K"): the K best
  * threshold passers by (score descending, scan position ascending), in that order - what a reader of

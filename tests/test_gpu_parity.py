@@ -526,7 +526,15 @@ def test_dropin_stage_functions(orc, c1_slot):
     cands = fd.ft8_find_candidates(wf, 20, 1)
     ct, cf, cs, _ = orc.ft8_find_candidates(mag, 2, 2, 20, 1)
     assert [(c.abs_time, c.abs_freq) for c in cands] == list(zip(ct.tolist(), cf.tolist()))
-    assert abs(fd.ft8_sync_score(wf, cands[0]) - cs[0]) < 1e-12
+    assert [c.score for c in cands] == cs.tolist()                      # returned scores: the reference's own sums, bit for bit
+    for c in cands[:4]:
+        assert fd.ft8_sync_score(wf, c) == orc.ft8_sync_score(mag, 2, 2, c.abs_time, c.abs_freq)
+    # ... also outside the range ft8_find_candidates scans (the reference function takes any position)
+    from ft8_demodulator_b200.ft8_demodulator.ftx_types import FT8Candidate
+    for at, af in ((-23, 7), (75, 1905), (-400, 3), (180, 100), (9, 1905)):
+        assert fd.ft8_sync_score(wf, FT8Candidate(waterfall=wf, abs_time=at, abs_freq=af)) == orc.ft8_sync_score(mag, 2, 2, at, af)
+    with pytest.raises(IndexError):
+        fd.ft8_sync_score(wf, FT8Candidate(waterfall=wf, abs_time=0, abs_freq=1906))
     ok, msg, st = fd.ft8_decode_candidate(wf, cands[0], 20)
     assert ok and bytes(msg.payload) == synth.C1_PAYLOAD and msg.hash == 7997 and st.ldpc_errors == 0
     ok2, msg2, st2 = fd.ft8_decode_candidate(wf, cands[1], 20)
@@ -1135,3 +1143,28 @@ def test_drift_sync_vs_cpu_statement(orc, F, T, s, b, hyps):
         fin = np.isfinite(ref)
         assert np.abs(g[fin] - ref[fin]).max() < 1e-12
         assert (h != ref_h).mean() < 1e-3          # another winner only between hypotheses that tie to rounding
+
+
+# ------------------------------------------------------------------------------------------ randomised differential runs
+def _tool(name):
+    import importlib
+    import os
+    import sys
+    tools = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools")
+    if tools not in sys.path:
+        sys.path.insert(0, tools)
+    return importlib.import_module(name)
+
+
+def test_fuzz_stage_functions():
+    """tools/fuzz_stages.py, short run: the stage-level mirrors on arbitrary waterfalls == the oracle, everything exact."""
+    out = _tool("fuzz_stages").run(80, 7)
+    assert out["n_failures"] == 0, out["failures"]
+    assert out["candidate_lists_compared"] >= 40 and out["candidate_decodes_compared"] >= 100
+
+
+def test_fuzz_whole_path():
+    """tools/fuzz_parity.py, short run: random geometries / parameters / input kinds through decode_slots == the oracle."""
+    out = _tool("fuzz_parity").run(14, 11)
+    assert not out["failures"], out["failures"]
+    assert out["candidate_records_compared"] >= 200

@@ -104,9 +104,7 @@ def compare(batch, ref_lists):
     return None
 
 
-def main():
-    trials = int(sys.argv[1]) if len(sys.argv) > 1 else 60
-    seed = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+def run(trials, seed):
     rng = np.random.default_rng(seed)
     failures, skipped, records, decoded = [], 0, 0, 0
     t0 = time.time()
@@ -140,9 +138,14 @@ def main():
         decoded += sum(1 for r in ref if r is not None for c in r if c["ok"])
         if why:
             failures.append(dict(desc, why=why))
-    print(json.dumps(dict(tool="fuzz_parity", trials=trials, seed=seed, skipped=skipped, candidate_records_compared=records,
-                          decodes_among_them=decoded, failures=failures, seconds=round(time.time() - t0, 1))))
-    sys.exit(1 if failures else 0)
+    return dict(tool="fuzz_parity", trials=trials, seed=seed, skipped=skipped, candidate_records_compared=records,
+                decodes_among_them=decoded, failures=failures, seconds=round(time.time() - t0, 1))
+
+
+def main():
+    out = run(int(sys.argv[1]) if len(sys.argv) > 1 else 60, int(sys.argv[2]) if len(sys.argv) > 2 else 0)
+    print(json.dumps(out))
+    sys.exit(1 if out["failures"] else 0)
 
 
 if __name__ == "__main__":
