@@ -1163,6 +1163,12 @@ def test_fuzz_stage_functions():
     assert out["candidate_lists_compared"] >= 40 and out["candidate_decodes_compared"] >= 100
 
 
+def test_fuzz_spectrogram():
+    """tools/fuzz_stages.py run_spectrogram, short run: calculate_spectrogram on random geometries / lengths / input types."""
+    out = _tool("fuzz_stages").run_spectrogram(40, 5)
+    assert out["n_failures"] == 0, out["failures"]
+
+
 def test_fuzz_whole_path():
     """tools/fuzz_parity.py, short run: random geometries / parameters / input kinds through decode_slots == the oracle."""
     out = _tool("fuzz_parity").run(14, 11)

@@ -110,10 +110,67 @@ def run(trials, seed):
                 seconds=round(time.time() - t0, 1))
 
 
+def run_spectrogram(trials, seed):
+    """calculate_spectrogram (mirror of spectrogram_analyse.py:19-66) on random geometries, lengths and input types against
+    a NumPy restatement of the scipy call it replaces (Hann, zero-padded FFT, |X|^2 / (sum w)^2, 10*log10(1e-12 + .),
+    fftshift): <= 1e-8 dB for float64 / complex128 input, 1e-4 for float32 / complex64 (the output is float32 there)."""
+    from ft8_demodulator_b200.ft8_demodulator import spectrogram_analyse as sa
+    rng = np.random.default_rng(seed)
+    fails, worst = [], 0.0
+    t0 = time.time()
+    for t in range(trials):
+        fs = rng.choice([2000, 3500, 4500, 6000, 7350, 8000, 9999.5, 10e3, 11025, 12000, 16000, 20000, 22050, 32768, 44100, 48000])
+        fs = float(fs) if fs != int(fs) else int(fs)
+        b, s = int(rng.integers(1, 6)), int(rng.integers(1, 9))
+        nperseg = int(0.16 * fs)
+        hop = nperseg - (nperseg - nperseg // s)
+        nfft = int(fs / 6.25 * b)
+        if nfft // 2 > 14336 or (nfft % 2 and nfft > 14336):
+            continue
+        n = int(rng.choice([nperseg - 1, nperseg, nperseg + 1, nperseg + hop - 1, nperseg + hop, int(nperseg * rng.uniform(1, 6))]))
+        kind = str(rng.choice(["f64", "f32", "c128", "c64", "i16"]))
+        x = rng.standard_normal(n) * 0.2 + np.cos(2 * np.pi * 0.07 * np.arange(n))
+        if kind in ("c128", "c64"):
+            x = x + 1j * rng.standard_normal(n) * 0.2
+        x = x.astype({"f64": np.float64, "f32": np.float32, "c128": np.complex128, "c64": np.complex64, "i16": np.float64}[kind])
+        if kind == "i16":
+            x = np.round(x * 1000).astype(np.int16)
+        desc = dict(trial=t, fs=fs, b=b, s=s, n=n, kind=kind, nperseg=nperseg, hop=hop, nfft=nfft)
+        try:
+            S, f, tt = sa.calculate_spectrogram(x, fs, b, s)
+        except NotImplementedError as e:
+            desc["unsupported"] = str(e)[:60]
+            continue
+        if n < nperseg:
+            if S.shape != (1, 0) or len(f) or len(tt):
+                fails.append(dict(desc, why="short input must give (array([[]]), [], [])"))
+            continue
+        win = 0.5 - 0.5 * np.cos(2 * np.pi * np.arange(nperseg) / nperseg)
+        T = (n - nperseg) // hop + 1
+        xw = x.astype(np.complex128 if np.iscomplexobj(x) else np.float64)
+        frames = np.stack([xw[j * hop:j * hop + nperseg] * win for j in range(T)])
+        ref = np.fft.fftshift(10 * np.log10(1e-12 + np.abs(np.fft.fft(frames, n=nfft, axis=1)) ** 2 / win.sum() ** 2).T, axes=0)
+        tol = 1e-4 if kind in ("f32", "c64") else 1e-8
+        want_dtype = np.float32 if kind in ("f32", "c64") else np.float64
+        if S.shape != ref.shape or S.dtype != want_dtype:
+            fails.append(dict(desc, why="shape/dtype %r %r vs %r" % (S.shape, S.dtype, ref.shape)))
+            continue
+        err = float(np.abs(S - ref).max())
+        worst = max(worst, err if tol == 1e-8 else 0.0)
+        if not err < tol:
+            fails.append(dict(desc, why="max |dB error| %g" % err))
+        if not (np.array_equal(f, np.fft.fftshift(np.fft.fftfreq(nfft, 1 / fs))) and len(tt) == T):
+            fails.append(dict(desc, why="axes differ"))
+    return dict(tool="fuzz_stages.spectrogram", trials=trials, seed=seed, worst_float64_db_error=worst, failures=fails[:20],
+                n_failures=len(fails), seconds=round(time.time() - t0, 1))
+
+
 def main():
     out = run(int(sys.argv[1]) if len(sys.argv) > 1 else 150, int(sys.argv[2]) if len(sys.argv) > 2 else 0)
     print(json.dumps(out))
-    sys.exit(1 if out["n_failures"] else 0)
+    out2 = run_spectrogram(int(sys.argv[1]) if len(sys.argv) > 1 else 150, int(sys.argv[2]) if len(sys.argv) > 2 else 0)
+    print(json.dumps(out2))
+    sys.exit(1 if out["n_failures"] or out2["n_failures"] else 0)
 
 
 if __name__ == "__main__":
