@@ -237,14 +237,21 @@ def case_rates():
     save("rates.npz", **arrays)
 
 
-def case_c4():
+C4_CASES = (("fs12000_k100", dict(fs=12000, drift_hz_s=100.0, esn0_db=40.0, seed=4)),
+            ("fs12000_k3", dict(fs=12000, drift_hz_s=3.3, esn0_db=30.0, seed=5)),
+            ("fs32768_k568", dict(fs=32768, drift_hz_s=568.0, esn0_db=35.0, seed=6)))
+# round 2: falling chirps, another carrier offset and sample rate
+C4B_CASES = (("fs12000_kneg60", dict(fs=12000, drift_hz_s=-60.0, esn0_db=35.0, seed=7, fc=2500.0)),
+             ("fs12000_kneg3", dict(fs=12000, drift_hz_s=-3.3, esn0_db=32.0, seed=8, f0=700.0, fc=900.0)),
+             ("fs20000_k250", dict(fs=20000, drift_hz_s=250.0, esn0_db=38.0, seed=9)))
+
+
+def case_c4(cases=C4_CASES, name="c4.npz"):
     """Config C4 (satellite pass): reference correct_frequency_drift + decode of the corrected real part
     (test_correction.py:281-336 parameters), two geometries."""
     FC = R.frequency_correction
     arrays = {}
-    for tag, cfg in (("fs12000_k100", dict(fs=12000, drift_hz_s=100.0, esn0_db=40.0, seed=4)),
-                     ("fs12000_k3", dict(fs=12000, drift_hz_s=3.3, esn0_db=30.0, seed=5)),
-                     ("fs32768_k568", dict(fs=32768, drift_hz_s=568.0, esn0_db=35.0, seed=6))):
+    for tag, cfg in cases:
         x = synth.c4_capture(**cfg)
         ridges, segs = [], []
         orig_spec, orig_det = FC.calculate_spectrogram, FC.detect_signal_continuity
@@ -282,7 +289,7 @@ def case_c4():
         arrays[tag + "__corrected_probe"] = corrected[::max(1, len(corrected) // 64)][:64]
         print("   c4 %s: drift %.6g Hz/s (true %.6g), %d decodes (correction %.0f s, decode %.0f s)" % (
             tag, float(np.asarray(rate).ravel()[0]) * cfg["fs"], cfg["drift_hz_s"], len(d["res_hash"]), t1 - t0, time.time() - t1))
-    save("c4.npz", **arrays)
+    save(name, **arrays)
 
 
 def case_ties():
@@ -309,7 +316,7 @@ def case_ties():
     save("ties.npz", **arrays)
 
 
-CASES = dict(ties=case_ties, c4=case_c4, kat=case_kat, c1=case_c1, bp=case_bp, wav=case_wav, c2=case_c2, rates=case_rates)
+CASES = dict(ties=case_ties, c4b=lambda: case_c4(C4B_CASES, "c4b.npz"), c4=case_c4, kat=case_kat, c1=case_c1, bp=case_bp, wav=case_wav, c2=case_c2, rates=case_rates)
 
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)

@@ -566,13 +566,15 @@ def test_edge_cases():
 
 
 # ------------------------------------------------------------------------------------------ satellite pre-processor
-@pytest.mark.parametrize("tag", ["fs12000_k3", "fs12000_k100", "fs32768_k568"])
+@pytest.mark.parametrize("tag", ["fs12000_k3", "fs12000_k100", "fs32768_k568", "fs12000_kneg60", "fs12000_kneg3", "fs20000_k250"])
 def test_drift_correction_golden(tag):
     """Config C4: correct_frequency_drift + decode of the corrected real part against the reference run recorded in
     tests/golden/c4.npz (payload-level parity per SURVEY 8d; ridge, segments and drift estimate checked as well)."""
     import hashlib
     from ft8_demodulator_b200.ft8_beacon_receiver import frequency_correction as fc
     g = load_golden("c4.npz")
+    if tag + "__cfg" not in g.files:
+        g = load_golden("c4b.npz")           # round 2: falling chirps, other carrier offsets, 20 kHz
     cfg = json.loads(str(g[tag + "__cfg"]))
     x = synth.c4_capture(**cfg)
     assert hashlib.sha256(np.ascontiguousarray(x).tobytes()).hexdigest() == str(g[tag + "__input_sha256"])
@@ -585,7 +587,7 @@ def test_drift_correction_golden(tag):
     assert np.mean(tr["ridge2"] == g[tag + "__ridge2"]) > 0.995        # second ridge sees a 1e-10-different waveform
     ref_rate = float(g[tag + "__drift_per_sample"])
     assert abs(rate - ref_rate) <= 1e-6 * abs(ref_rate)
-    assert abs(rate * cfg["fs"] - cfg["drift_hz_s"]) < 0.05 * cfg["drift_hz_s"] + 0.2
+    assert abs(rate * cfg["fs"] - cfg["drift_hz_s"]) < 0.05 * abs(cfg["drift_hz_s"]) + 0.2
     probe = corrected[::max(1, len(corrected) // 64)][:64]
     assert corrected.dtype == np.complex128 and np.abs(probe - g[tag + "__corrected_probe"]).max() < 1e-6
     gold = golden_case(g, tag)

@@ -153,10 +153,10 @@ def test_pack_records_layout():
 def test_drift_host_logic_on_golden_ridge():
     """detect_signal_continuity on the reference's own ridge (tests/golden/c4.npz) reproduces its segments."""
     from ft8_demodulator_b200.ft8_beacon_receiver import frequency_correction as fc
-    g = load_golden("c4.npz")
-    for tag in ("fs12000_k100", "fs12000_k3", "fs32768_k568"):
+    for tag in ("fs12000_k100", "fs12000_k3", "fs32768_k568", "fs12000_kneg60", "fs12000_kneg3", "fs20000_k250"):
+        g = load_golden("c4b.npz" if tag in ("fs12000_kneg60", "fs12000_kneg3", "fs20000_k250") else "c4.npz")
         ridge = g[tag + "__ridge1"]
-        n_pos = {"fs12000": 1920, "fs32768": 5243}[tag.split("_")[0]]
+        n_pos = {"fs12000": 1920, "fs32768": 5243, "fs20000": 3200}[tag.split("_")[0]]
         segs, metric = fc.detect_signal_continuity(ridge, window_size=4 * 8, max_variance=0.0001 * n_pos ** 2)
         assert [list(s) for s in segs] == g[tag + "__segments"].tolist()
         assert len(metric) == len(ridge) - 32 + 1
