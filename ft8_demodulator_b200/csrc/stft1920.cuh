@@ -312,16 +312,39 @@ __global__ void __launch_bounds__(kStft1920Threads, MB) stft1920_kernel(const St
     WaveT *xs = reinterpret_cast<WaveT *>(tw2s + 16 * 15);        // [1920]
 #endif
     const int tid = threadIdx.x;
+    // The tables (33 KB per CTA) are staged with 16-byte cp.async copies: all 17 copies of a thread are in flight at
+    // once and land under the first frame's audio staging (one wait + barrier below covers both).  A load-then-store
+    // loop keeps ONE load in flight per thread and iteration - 17 L2 round trips, as long as a whole frame takes,
+    // which is half of a single-slot call (one frame per CTA) and 3 % of the 4096-slot batch.
+    auto copy16 = [](void *dst, const void *src) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+    };
 #if FT8B_STFT_SMEMTAB
-    for (int i = tid; i < 7 * kTw3Cols; i += kStft1920Threads) {
-        const int t = i / kTw3Cols + 1, j = i - (t - 1) * kTw3Cols;
-        tw3s[i] = __ldg(&a.tw3[t * kTw3Stride + j]);
+#pragma unroll
+    for (int r = 0; r < (7 * kTw3Cols + kStft1920Threads - 1) / kStft1920Threads; ++r) {
+        const int i = tid + r * kStft1920Threads;
+        if (i < 7 * kTw3Cols) {
+            const int t = i / kTw3Cols + 1, j = i - (t - 1) * kTw3Cols;
+            copy16(&tw3s[i], &a.tw3[t * kTw3Stride + j]);
+        }
     }
-    for (int i = tid; i < kTwpLen; i += kStft1920Threads) twps[i] = __ldg(&a.twpost[i]);
+#pragma unroll
+    for (int r = 0; r < (kTwpLen + kStft1920Threads - 1) / kStft1920Threads; ++r) {
+        const int i = tid + r * kStft1920Threads;
+        if (i < kTwpLen) copy16(&twps[i], &a.twpost[i]);
+    }
 #endif
-    for (int i = tid; i < 512; i += kStft1920Threads) logtab8[i] = __ldg(&a.logtab[i >> 3]);
+#pragma unroll
+    for (int r = 0; r < 512 / kStft1920Threads; ++r) {
+        const int i = tid + r * kStft1920Threads;
+        copy16(&logtab8[i], &a.logtab[i >> 3]);
+    }
     const double2 *logtab = logtab8 + (tid & 7);                  // this lane's copy
-    for (int i = tid; i < 16 * 15; i += kStft1920Threads) tw2s[i] = __ldg(&a.tw2[i]);
+#pragma unroll
+    for (int r = 0; r < (16 * 15 + kStft1920Threads - 1) / kStft1920Threads; ++r) {
+        const int i = tid + r * kStft1920Threads;
+        if (i < 16 * 15) copy16(&tw2s[i], &a.tw2[i]);
+    }
     const int64_t n_items = a.n_slots * a.frames_out;
     const int Fout = a.bin_hi - a.bin_lo;
     const double scale4 = 0.25 * a.scale;
@@ -363,7 +386,7 @@ __global__ void __launch_bounds__(kStft1920Threads, MB) stft1920_kernel(const St
         __pipeline_commit();
     };
     stage_audio(blockIdx.x);
-    if (VEC) __pipeline_wait_prior(0);
+    __pipeline_wait_prior(0);           // tables + (VEC) the first frame's audio
     __syncthreads();
 #else
     // Each thread copies exactly the sample pairs it will consume in P1 (n = tid + 128 t), so waiting on its own
@@ -381,6 +404,7 @@ __global__ void __launch_bounds__(kStft1920Threads, MB) stft1920_kernel(const St
         __pipeline_commit();
     };
     stage_audio(blockIdx.x);
+    __pipeline_wait_prior(0);           // the tables (this thread's first audio pairs ride along)
     __syncthreads();
 #endif
     FT8B_PROF_DECL
