@@ -828,7 +828,37 @@ static bool sync_uses_lap(int b) {
     return b == 2 && env_lap && env_lap[0] == '1';
 }
 
-// strips per slot the pair kernels summarise (0 when the geometry runs on sync_scores_kernel, which does not)
+// Shared memory the walk kernels need for nu time offsets per phase (their score sums live there), and what a CTA may
+// have.  Captures longer than ~42 s (nu > 213 at freq_osr 2) do not fit: they run on sync_scores_direct_kernel below.
+static size_t sync_walk_smem(int nu, int b, bool pair, bool lap) {
+    if (lap) return sync_lap_smem_bytes(nu);
+    if (pair) return b == 1 ? sync_pair_smem_bytes<1>(nu) : b == 2 ? sync_pair_smem_bytes<2>(nu) : sync_pair_smem_bytes<4>(nu);
+    return sizeof(double) * ((size_t)nu * kSyncThreads + (size_t)(kSyncThreads / 32) * kSyncStages * (32 + 7 * b)) +
+           sizeof(double2) * (size_t)nu;
+}
+static size_t sync_smem_limit() {
+    int dev = 0, max_smem = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) {
+        cudaGetLastError();              // host-only workspace queries (no device): the sm_100 figure, 227 KB
+        return 227 * 1024;
+    }
+    return (size_t)max_smem;
+}
+
+// ft8_sync_score for EVERY position of the search range, one thread per score, each the reference's own running sum
+// (ref_sync_score): no shared state, any number of time offsets - the path of captures too long for the walk kernels'
+// score sums (and bit-equal to the reference on the same spectrogram, where the walks are within 1e-12).
+__global__ void sync_scores_direct_kernel(const SyncArgs a, int t0) {
+    const int64_t per_slot = (int64_t)a.nu * a.s * a.nf;
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= per_slot) return;
+    const int64_t slot = blockIdx.y;
+    const int row = (int)(i / a.nf), f = (int)(i - (int64_t)row * a.nf);
+    a.scores[slot * per_slot + i] = ref_sync_score(a.mag + slot * (int64_t)a.T * a.F, a.F, a.s, a.b, a.nb, t0 + row, f);
+}
+
+// strips per slot the pair kernels summarise (0 when the geometry runs on a kernel that leaves none)
 int sync_tiles_per_slot(int T, int F, int s, int b) {
     int t0, nt, nf;
     ft8b_search_ranges(T, F, s, b, &t0, &nt, &nf);
@@ -837,6 +867,7 @@ int sync_tiles_per_slot(int T, int F, int s, int b) {
     if (nt <= 0 || nf <= 0 || !(b == 1 || b == 2 || b == 4) || (env_single && env_single[0] == '1') ||
         (env_scan && env_scan[0] == '1'))
         return 0;
+    if (sync_walk_smem(nt / s, b, true, sync_uses_lap(b)) > sync_smem_limit()) return 0;      // direct kernel: no strips
     if (sync_uses_lap(b)) return s * ((sync_lap_warps(nf) + 1) / 2) * (kLapThreads / 32);
     return s * ((nf + kPairCols - 1) / kPairCols) * (kPairThreads / 32);
 }
@@ -862,6 +893,19 @@ int sync_scores(const double *mag, int64_t n_slots, int T, int F, int s, int b, 
     const char *env_single = getenv("FT8B_SYNC_SINGLE");            // "1": one candidate per thread for every freq_osr
     const bool single = env_single && env_single[0] == '1';
     const bool pair = (b == 1 || b == 2 || b == 4) && !single;      // two candidates per thread (sync_pair.cuh)
+    if (sync_walk_smem(a.nu, b, pair, pair && sync_uses_lap(b)) > (size_t)max_smem) {
+        // too many time offsets for the score sums of a walk (a capture of more than ~42 s): one thread per score
+        if (tiles) FT8B_ARG_FAIL("sync_scores: strip summaries are only produced by the pair kernels");
+        const int64_t per_slot = (int64_t)nt * nf;
+        if (n_slots > 65535) {
+            set_error("ft8b_sync_scores: slots per call must be <= 65535");
+            return FT8B_ERR_UNSUPPORTED;
+        }
+        dim3 grid((unsigned)((per_slot + 255) / 256), (unsigned)n_slots);
+        sync_scores_direct_kernel<<<grid, 256, 0, stream>>>(a, t0);
+        FT8B_LAUNCH_CHECK("sync_scores_direct_kernel");
+        return 0;
+    }
     if (pair && sync_uses_lap(b)) {
         const size_t smem_l = sync_lap_smem_bytes(a.nu);
         if (smem_l > (size_t)max_smem) {

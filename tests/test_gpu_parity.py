@@ -1147,6 +1147,40 @@ def test_drift_sync_vs_cpu_statement(orc, F, T, s, b, hyps):
         assert (h != ref_h).mean() < 1e-3          # another winner only between hypotheses that tie to rounding
 
 
+def test_long_capture_beyond_the_walk_kernels(orc):
+    """A 60-s capture (374 symbols, 325 time offsets per phase) does not fit the score sums of the walk kernels in shared
+    memory (limit ~42 s): the score map then comes from sync_scores_direct_kernel, one thread per score in the
+    reference's own summation order - bit-equal to the oracle's map on the same spectrogram -, and the whole decode
+    equals the oracle's record by record."""
+    rng = np.random.default_rng(60)
+    fs, n = 12000, 60 * 12000
+    x = rng.standard_normal(n) * 0.5
+    payloads = []
+    for k, (f0, start) in enumerate(((600.0, 3.0), (1500.0, 20.5), (2200.0, 44.0))):
+        pl = bytes(rng.integers(0, 256, 9, dtype=np.uint8)) + bytes([int(rng.integers(0, 32)) << 3])
+        payloads.append(pl)
+        burst = synth.ft8_generator(pl, fs, f0)
+        x[int(start * fs):int(start * fs) + len(burst)] += burst * 0.5
+    x = x.astype(np.float32)
+    mag = orc.spectrogram_pos(x.astype(np.float64), fs, 2, 2)                       # [F, T]
+    dev_mag = engine._dev(np.ascontiguousarray(mag.T).reshape(1, mag.shape[1], mag.shape[0]))
+    scores, t0 = engine.sync_scores(dev_mag, 2, 2)
+    ref_map = orc.score_map(mag, 2, 2)
+    assert scores.shape[1] == ref_map.shape[0] == 650 and t0 == -20
+    assert np.array_equal(scores[0].cpu().numpy(), ref_map, equal_nan=True)
+    kw = dict(max_candidates=300, min_score=6.0, max_iterations=20)
+    batch = fd.decode_slots(np.stack([x, x[::-1].copy()]), fs, 2, 2, **kw)
+    for i, w in enumerate((x, x[::-1].copy())):
+        ref = orc.decode_all_candidates(w.astype(np.float64), fs, 2, 2, 300, 6.0, 20)
+        a = batch.arrays
+        assert int(a.n_cand[i]) == len(ref)
+        for c, r in enumerate(ref):
+            assert (int(a.cand_time[i, c]), int(a.cand_freq[i, c]), bool(a.ok[i, c]), int(a.ldpc_errors[i, c]),
+                    bytes(a.payload[i, c].numpy())) == (r["abs_time"], r["abs_freq"], r["ok"], r["ldpc_errors"], r["payload"])
+            assert abs(float(a.cand_score[i, c]) - r["score"]) < SCORE_TOL
+    assert set(payloads) <= batch.payload_sets()[0]
+
+
 # ------------------------------------------------------------------------------------------ randomised differential runs
 def _tool(name):
     import importlib

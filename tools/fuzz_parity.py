@@ -27,7 +27,7 @@ def draw_trial(rng):
     fs = int(rng.choice(RATES))
     b = int(rng.choice([1, 2, 2, 2, 3, 4]))
     s = int(rng.choice([1, 2, 2, 2, 3, 4, 5]))
-    dur = float(rng.choice([10.0, 12.7, 13.0, 14.0, 15.0, 15.0, 15.0, 16.5]))
+    dur = float(rng.choice([10.0, 12.7, 13.0, 14.0, 15.0, 15.0, 15.0, 16.5, 30.0, 47.0]))
     n = int(fs * dur) + int(rng.integers(0, 7))
     B = int(rng.integers(1, 6))
     kw = dict(max_candidates=int(rng.choice([1, 2, 5, 20, 20, 64, 65, 150])),
