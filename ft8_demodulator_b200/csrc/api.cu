@@ -318,7 +318,11 @@ int ft8b_decode_slots(const void *wave, int wave_dtype, int64_t n_slots, int64_t
     // crc_extracted / crc_calculated may be NULL (not wanted); every other array is required
     if (!p || !wave || !workspace || !cand_time || !cand_freq || !cand_score || !n_cand || !ok || !ldpc_errors || !payload)
         FT8B_ARG_FAIL("ft8b_decode_slots: null pointer");
-    if (wave_dtype != FT8B_DTYPE_F32 && wave_dtype != FT8B_DTYPE_F64 && wave_dtype != FT8B_DTYPE_I16) FT8B_ARG_FAIL("ft8b_decode_slots: bad dtype");
+    // complex audio (the reference takes it too: two-sided spectrogram, rows f >= 0 kept - ft8_decode.py:316-325) runs a
+    // full-length complex transform in the STFT stage; everything after the spectrogram is the same
+    if (wave_dtype != FT8B_DTYPE_F32 && wave_dtype != FT8B_DTYPE_F64 && wave_dtype != FT8B_DTYPE_I16 &&
+        wave_dtype != FT8B_DTYPE_C64 && wave_dtype != FT8B_DTYPE_C128)
+        FT8B_ARG_FAIL("ft8b_decode_slots: bad dtype");
     if (p->max_candidates < 0 || p->max_candidates > FT8B_MAX_CANDIDATES) {
         set_error("ft8b_decode_slots: max_candidates=%d outside [0,%d]", p->max_candidates, FT8B_MAX_CANDIDATES);
         return FT8B_ERR_UNSUPPORTED;
@@ -328,7 +332,7 @@ int ft8b_decode_slots(const void *wave, int wave_dtype, int64_t n_slots, int64_t
     if (rc) return rc;
     if (n_slots <= 0) return 0;
     const int K = p->max_candidates;
-    const size_t elt = wave_dtype == FT8B_DTYPE_F32 ? 4 : (wave_dtype == FT8B_DTYPE_I16 ? 2 : 8);
+    const size_t elt = wave_dtype == FT8B_DTYPE_F32 ? 4 : wave_dtype == FT8B_DTYPE_I16 ? 2 : wave_dtype == FT8B_DTYPE_C128 ? 16 : 8;
     if (g.T <= 0 || g.F <= 0 || g.score_elems == 0 || K == 0) {
         // nothing to search: the reference returns an empty list.  Every output array is defined (zeros), as after a
         // search that found nothing - a direct C caller may pass uninitialised buffers.

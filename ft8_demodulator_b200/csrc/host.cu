@@ -295,7 +295,7 @@ struct HostCall {
 int host_call(HostPath &h, const HostCall &c) {
     const ft8b_decode_params *p = c.p;
     const int64_t n_slots = c.n_slots, K = p->max_candidates;
-    const size_t elt = c.wave_dtype == FT8B_DTYPE_F32 ? 4 : (c.wave_dtype == FT8B_DTYPE_I16 ? 2 : 8);
+    const size_t elt = c.wave_dtype == FT8B_DTYPE_F32 ? 4 : c.wave_dtype == FT8B_DTYPE_I16 ? 2 : c.wave_dtype == FT8B_DTYPE_C128 ? 16 : 8;
     const size_t row_bytes = (size_t)c.n_samples * elt, src_pitch = (size_t)c.slot_stride * elt;
     const int64_t piece = std::min<int64_t>(n_slots, c.piece_slots > 0 ? c.piece_slots : 256);
     // ft8b_decode_workspace_bytes(piece) covers every batch of at most `piece` slots, i.e. the shorter tail piece too
@@ -425,7 +425,8 @@ extern "C" int ft8b_decode_slots_host(const void *wave, int wave_dtype, int64_t 
     // crc_extracted / crc_calculated may be NULL (not wanted), as in ft8b_decode_slots; every other array is required
     if (!p || (!wave && n_slots > 0) || !cand_time || !cand_freq || !cand_score || !n_cand || !ok || !ldpc_errors || !payload)
         FT8B_ARG_FAIL("ft8b_decode_slots_host: null pointer");
-    if (wave_dtype != FT8B_DTYPE_F32 && wave_dtype != FT8B_DTYPE_F64 && wave_dtype != FT8B_DTYPE_I16)
+    if (wave_dtype != FT8B_DTYPE_F32 && wave_dtype != FT8B_DTYPE_F64 && wave_dtype != FT8B_DTYPE_I16 &&
+        wave_dtype != FT8B_DTYPE_C64 && wave_dtype != FT8B_DTYPE_C128)
         FT8B_ARG_FAIL("ft8b_decode_slots_host: bad dtype");
     if (n_slots < 0 || n_samples < 0 || slot_stride < n_samples) FT8B_ARG_FAIL("ft8b_decode_slots_host: bad shape");
     if (p->max_candidates < 0 || p->max_candidates > FT8B_MAX_CANDIDATES) {

@@ -246,7 +246,8 @@ def decode_slots(waves, sample_rate, bins_per_tone: int = 2, steps_per_symbol: i
                  min_score=10, max_iterations: int = 20, freq_min=None, freq_max=None, time_min=None, time_max=None,
                  chunk_slots: int = 0, return_device: bool = False, piece_slots: int = 256, pcm16: bool = False,
                  strict_topk: bool = False):
-    """Decode a batch of equal-length slots: waves [B, N] (NumPy or torch, host or device, float32/float64).
+    """Decode a batch of equal-length slots: waves [B, N] (NumPy or torch, host or device, float32/float64, or
+    complex64/complex128 baseband - the reference keeps the f >= 0 rows of the two-sided spectrogram then).
 
     With pcm16=True an int16 array is taken as PCM and normalised on the GPU as float32(x)/32767, the way the
     reference's WAV reader does on the host (src/tests/demodulator/from_wave.py:62-66) - half the host-to-device
@@ -259,14 +260,18 @@ def decode_slots(waves, sample_rate, bins_per_tone: int = 2, steps_per_symbol: i
     dev = engine.require_cuda()
     if isinstance(waves, np.ndarray):
         if np.iscomplexobj(waves):
-            raise NotImplementedError("complex input is not covered by the CUDA STFT yet (real audio only)")
-        if waves.dtype not in (np.float32, np.float64) and not (pcm16 and waves.dtype == np.int16):
+            # complex baseband, as the reference's SDR receive script passes it (src/tests/pluto-sdr/receive.py:68-78):
+            # two-sided spectrogram, rows f >= 0 kept (ft8_decode.py:316-325) - a full-length complex transform in S1
+            if waves.dtype != np.complex64:
+                waves = waves.astype(np.complex128)
+        elif waves.dtype not in (np.float32, np.float64) and not (pcm16 and waves.dtype == np.int16):
             waves = waves.astype(np.float64)
         waves = np.ascontiguousarray(waves)
         waves = torch.from_numpy(waves if waves.flags.writeable else waves.copy())
     if waves.dim() == 1:
         waves = waves.reshape(1, -1)
-    if waves.dtype not in (torch.float32, torch.float64) and not (pcm16 and waves.dtype == torch.int16):
+    if waves.dtype not in (torch.float32, torch.float64, torch.complex64, torch.complex128) and \
+            not (pcm16 and waves.dtype == torch.int16):
         waves = waves.to(torch.float64)
     B, N = waves.shape
     g = decode_geometry(N, sample_rate, bins_per_tone, steps_per_symbol, freq_min, freq_max, time_min, time_max)
@@ -346,7 +351,11 @@ def decode_ft8_message(wave_data: np.ndarray, sample_rate: int, bins_per_tone: i
     (FT8Message, FT8DecodeStatus, time_sec, freq_hz, score) in candidate (score-descending) order, with
     time_sec = abs_time / sample_rate and freq_hz = abs_freq / bins_per_tone * 6.25 as the reference defines them.
     strict_topk is the one extra keyword (default off = the reference's candidate list), see decode_slots."""
-    x = _as_real_audio(wave_data)
+    if np.iscomplexobj(wave_data):
+        x = np.asarray(wave_data).reshape(-1)
+        x = np.ascontiguousarray(x if x.dtype == np.complex64 else x.astype(np.complex128))
+    else:
+        x = _as_real_audio(wave_data)
     nperseg, _, _ = _lib.plan(sample_rate, bins_per_tone, steps_per_symbol)
     if len(x) < nperseg:
         return []

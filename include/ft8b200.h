@@ -48,7 +48,8 @@ extern "C" {
 #define FT8B_DTYPE_F32 0
 #define FT8B_DTYPE_F64 1
 #define FT8B_DTYPE_I16 2   /* int16 PCM, normalised on load as float32(x) / 32767.0f (from_wave.py:62-66) */
-#define FT8B_DTYPE_C64 3   /* complex64 (interleaved re,im float32): ft8b_stft_db only, all nfft bins, natural FFT order */
+#define FT8B_DTYPE_C64 3   /* complex64 (interleaved re,im float32): ft8b_stft_db (all nfft bins, natural FFT order) and the
+                              decode entry points (bins 0 .. (nfft+1)/2 - 1 = the reference's f >= 0 rows, ft8_decode.py:323-325) */
 #define FT8B_DTYPE_C128 4  /* complex128 */
 
 #define FT8B_LDPC_N 174

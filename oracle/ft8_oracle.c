@@ -119,7 +119,7 @@ static void dft_rec(const cplx *in, int stride, cplx *out, int n, const cplx *tw
  * exactly like the reference's `spectrogram[positive_freq_mask]`.
  *   spectrogram_analyse.py:46-56 (scipy call) and :59-60 (10*log10(1e-12+|S|)).
  */
-int orc_spectrogram_pos(const double *x, long n, int nperseg, int hop, int nfft, double *mag) {
+static int spectrogram_pos_impl(const double *x, int cplx_in, long n, int nperseg, int hop, int nfft, double *mag) {
     long T = orc_num_frames(n, nperseg, hop);
     if (T <= 0 || nfft < nperseg) return ORC_ERR_ARG;
     int F = (nfft + 1) / 2;
@@ -142,8 +142,13 @@ int orc_spectrogram_pos(const double *x, long n, int nperseg, int hop, int nfft,
     }
     double scale = 1.0 / (wsum * wsum);  /* scaling='spectrum' */
     for (long j = 0; j < T; j++) {
-        const double *fr = x + j * hop;
-        for (int i = 0; i < nperseg; i++) { buf[i].re = w[i] * fr[i]; buf[i].im = 0.0; }
+        if (cplx_in) {   /* complex audio, interleaved (re, im): same scipy call, two-sided either way */
+            const double *fr = x + 2 * j * hop;
+            for (int i = 0; i < nperseg; i++) { buf[i].re = w[i] * fr[2 * i]; buf[i].im = w[i] * fr[2 * i + 1]; }
+        } else {
+            const double *fr = x + j * hop;
+            for (int i = 0; i < nperseg; i++) { buf[i].re = w[i] * fr[i]; buf[i].im = 0.0; }
+        }
         for (int i = nperseg; i < nfft; i++) { buf[i].re = 0.0; buf[i].im = 0.0; }
         dft_rec(buf, 1, out, nfft, tw, nfft, tmp);
         for (int k = 0; k < F; k++) {
@@ -153,6 +158,14 @@ int orc_spectrogram_pos(const double *x, long n, int nperseg, int hop, int nfft,
     }
     free(tw); free(buf); free(out); free(tmp); free(w);
     return 0;
+}
+
+int orc_spectrogram_pos(const double *x, long n, int nperseg, int hop, int nfft, double *mag) {
+    return spectrogram_pos_impl(x, 0, n, nperseg, hop, nfft, mag);
+}
+/* complex audio x[2n] = (re, im) pairs: the rows f >= 0 of the two-sided spectrogram (ft8_decode.py:323-325) */
+int orc_spectrogram_pos_c(const double *x, long n, int nperseg, int hop, int nfft, double *mag) {
+    return spectrogram_pos_impl(x, 1, n, nperseg, hop, nfft, mag);
 }
 
 /* ------------------------------------------------------------------------------------ */
@@ -554,10 +567,10 @@ int orc_masks(double fs, int nperseg, int hop, int nfft, long T, double freq_min
  * candidate (score-descending) order; the reference's return list is the subset with ok==1.
  * Returns the number of candidates, or a negative error.  T_out and F_out report the waterfall shape.
  */
-int orc_decode_message(const double *wave, long n, double fs, int bins_per_tone, int steps_per_symbol,
-                       int max_candidates, double min_score, int max_iterations, double freq_min,
-                       double freq_max, double time_min, double time_max, orc_record *records, int max_records,
-                       int *F_out, int *T_out) {
+static int decode_message_impl(const double *wave, int cplx_in, long n, double fs, int bins_per_tone, int steps_per_symbol,
+                               int max_candidates, double min_score, int max_iterations, double freq_min,
+                               double freq_max, double time_min, double time_max, orc_record *records, int max_records,
+                               int *F_out, int *T_out) {
     int nperseg, hop, nfft;
     orc_plan(fs, bins_per_tone, steps_per_symbol, &nperseg, &hop, &nfft);
     long T = orc_num_frames(n, nperseg, hop);
@@ -565,7 +578,7 @@ int orc_decode_message(const double *wave, long n, double fs, int bins_per_tone,
     int Fpos = (nfft + 1) / 2;
     double *full = (double *)malloc(sizeof(double) * (size_t)Fpos * (size_t)T);
     if (!full) return ORC_ERR_ARG;
-    int rc = orc_spectrogram_pos(wave, n, nperseg, hop, nfft, full);
+    int rc = spectrogram_pos_impl(wave, cplx_in, n, nperseg, hop, nfft, full);
     if (rc) { free(full); return rc; }
     int k_lo, k_hi;
     long j_lo, j_hi;
@@ -592,6 +605,22 @@ int orc_decode_message(const double *wave, long n, double fs, int bins_per_tone,
     }
     free(ct); free(cf); free(cs); free(mag);
     return nc;
+}
+
+int orc_decode_message(const double *wave, long n, double fs, int bins_per_tone, int steps_per_symbol,
+                       int max_candidates, double min_score, int max_iterations, double freq_min,
+                       double freq_max, double time_min, double time_max, orc_record *records, int max_records,
+                       int *F_out, int *T_out) {
+    return decode_message_impl(wave, 0, n, fs, bins_per_tone, steps_per_symbol, max_candidates, min_score, max_iterations,
+                               freq_min, freq_max, time_min, time_max, records, max_records, F_out, T_out);
+}
+/* the same for complex audio (n complex samples, interleaved) */
+int orc_decode_message_c(const double *wave, long n, double fs, int bins_per_tone, int steps_per_symbol,
+                         int max_candidates, double min_score, int max_iterations, double freq_min,
+                         double freq_max, double time_min, double time_max, orc_record *records, int max_records,
+                         int *F_out, int *T_out) {
+    return decode_message_impl(wave, 1, n, fs, bins_per_tone, steps_per_symbol, max_candidates, min_score, max_iterations,
+                               freq_min, freq_max, time_min, time_max, records, max_records, F_out, T_out);
 }
 
 /* ---- batch entry points (CPU baseline legs of bench.py): pthreads, dynamic work queue ---- */

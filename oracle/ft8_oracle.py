@@ -69,6 +69,8 @@ def lib():
         L.orc_decode_message.argtypes = [dp, C.c_long, C.c_double, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int,
                                          C.c_double, C.c_double, C.c_double, C.c_double, C.POINTER(Record), C.c_int,
                                          ip, ip]
+        L.orc_decode_message_c.argtypes = L.orc_decode_message.argtypes
+        L.orc_spectrogram_pos_c.argtypes = L.orc_spectrogram_pos.argtypes
         L.orc_decode_batch.argtypes = [dp, C.c_long, C.c_long, C.c_double, C.c_int, C.c_int, C.c_int, C.c_double,
                                        C.c_int, C.POINTER(Record), ip, C.c_int]
         L.orc_bp_batch.argtypes = [dp, C.c_long, C.c_int, C.POINTER(C.c_uint8), C.POINTER(C.c_int32), C.c_int]
@@ -356,12 +358,16 @@ def masks(sample_rate, nperseg, hop, nfft, T, freq_min=None, freq_max=None, time
 
 def decode_all_candidates(wave, sample_rate, bins_per_tone=2, steps_per_symbol=2, max_candidates=20, min_score=10,
                           max_iterations=20, freq_min=None, freq_max=None, time_min=None, time_max=None):
-    """Records (dicts) for ALL candidates in the reference's candidate order."""
-    x = _f64(wave)
+    """Records (dicts) for ALL candidates in the reference's candidate order.  Complex audio (the reference keeps the
+    f >= 0 rows of its two-sided spectrogram, ft8_decode.py:323-325) goes in as interleaved (re, im) float64."""
+    cplx = np.iscomplexobj(wave)
+    x = np.ascontiguousarray(np.asarray(wave, dtype=np.complex128).reshape(-1)).view(np.float64) if cplx else _f64(wave)
+    n_samples = len(x) // 2 if cplx else len(x)
     K = int(max_candidates)
     recs = (Record * max(K, 1))()
     F, T = C.c_int(), C.c_int()
-    n = lib().orc_decode_message(_dp(x), len(x), float(sample_rate), bins_per_tone, steps_per_symbol, K,
+    fn = lib().orc_decode_message_c if cplx else lib().orc_decode_message
+    n = fn(_dp(x), n_samples, float(sample_rate), bins_per_tone, steps_per_symbol, K,
                                  float(min_score), max_iterations, _none_nan(freq_min), _none_nan(freq_max),
                                  _none_nan(time_min), _none_nan(time_max), recs, K, C.byref(F), C.byref(T))
     if n == ERR_TIE:

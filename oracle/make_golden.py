@@ -316,7 +316,28 @@ def case_ties():
     save("ties.npz", **arrays)
 
 
-CASES = dict(ties=case_ties, c4b=lambda: case_c4(C4B_CASES, "c4b.npz"), c4=case_c4, kat=case_kat, c1=case_c1, bp=case_bp, wav=case_wav, c2=case_c2, rates=case_rates)
+def case_cplx():
+    """Complex baseband input to decode_ft8_message (the reference's SDR receive script does this,
+    src/tests/pluto-sdr/receive.py:68-78): two-sided spectrogram, rows f >= 0 kept (ft8_decode.py:316-325)."""
+    arrays = {}
+    for tag, cfg, kw in (("c12000", dict(fs=12000, drift_hz_s=0.0, esn0_db=30.0, seed=12, f0=300.0, fc=500.0),
+                          dict(max_candidates=20, min_score=6, max_iterations=20)),
+                         ("c12000_band", dict(fs=12000, drift_hz_s=0.0, esn0_db=24.0, seed=13, f0=450.0, fc=900.0),
+                          dict(max_candidates=60, min_score=4, max_iterations=20, freq_min=600.0, freq_max=2400.0, time_min=8.0)),
+                         ("c6000", dict(fs=6000, drift_hz_s=0.0, esn0_db=28.0, seed=14, f0=200.0, fc=700.0),
+                          dict(max_candidates=20, min_score=5, max_iterations=10))):
+        x = synth.c4_capture(**cfg)
+        t0 = time.time()
+        d = traced_decode(x, cfg["fs"], llr_keep=2, bins_per_tone=2, steps_per_symbol=2, **kw)
+        arrays.update(prefixed(tag + "__", d))
+        arrays[tag + "__cfg"] = np.array(json.dumps(cfg))
+        arrays[tag + "__kw"] = np.array(json.dumps(kw))
+        arrays[tag + "__input_sha256"] = np.array(sha(x))
+        print("   cplx %s: %d cands, %d decodes (%.0f s)" % (tag, len(d["cand_time"]), len(d["res_hash"]), time.time() - t0))
+    save("cplx.npz", **arrays)
+
+
+CASES = dict(cplx=case_cplx, ties=case_ties, c4b=lambda: case_c4(C4B_CASES, "c4b.npz"), c4=case_c4, kat=case_kat, c1=case_c1, bp=case_bp, wav=case_wav, c2=case_c2, rates=case_rates)
 
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)

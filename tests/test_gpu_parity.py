@@ -104,8 +104,6 @@ def test_complex_input_spectrogram(fs, b, s, n):
     fr64 = np.stack([x64[j * hop:j * hop + nperseg].astype(np.complex128) * win for j in range(T)])
     ref64 = np.fft.fftshift(10 * np.log10(1e-12 + np.abs(np.fft.fft(fr64, n=nfft, axis=1)) ** 2 / win.sum() ** 2).T, axes=0)
     assert S64.dtype == np.float32 and np.abs(S64 - ref64).max() < 1e-4
-    with pytest.raises(NotImplementedError):
-        fd.decode_ft8_message(x, fs)
 
 
 def test_stft_signal_floor():
@@ -420,6 +418,35 @@ def test_c2_golden(tag, kw):
     if tag == "k2000_s3":
         decoded = batch.payload_sets()[0]
         assert decoded == set(bytes(p) for p in gold["res_payload"]) and len(decoded & set(payloads)) >= 20
+
+
+@pytest.mark.parametrize("tag", ["c12000", "c12000_band", "c6000"])
+def test_complex_input_golden(orc, tag):
+    """Complex baseband through decode_slots / decode_ft8_message (full-length complex transform in S1, rows f >= 0 kept)
+    against the traced reference runs of tests/golden/cplx.npz; complex64 input against the oracle on the widened values;
+    NumPy, pinned and device-resident input give the same arrays."""
+    g = load_golden("cplx.npz")
+    cfg, kw = json.loads(str(g[tag + "__cfg"])), json.loads(str(g[tag + "__kw"]))
+    x = synth.c4_capture(**cfg)
+    gold = golden_case(g, tag)
+    batch = fd.decode_slots(x.reshape(1, -1), cfg["fs"], 2, 2, **kw)
+    check_against_gold(batch.arrays, gold)
+    check_result_list(fd.decode_ft8_message(x, cfg["fs"], 2, 2, **kw), gold)
+    dev_in = fd.decode_slots(torch.from_numpy(x.reshape(1, -1)).cuda(), cfg["fs"], 2, 2, **kw)
+    for f in batch.arrays.__dataclass_fields__:
+        assert torch.equal(getattr(batch.arrays, f), getattr(dev_in.arrays, f)), f
+    x64 = x.astype(np.complex64)
+    b64 = fd.decode_slots(np.stack([x64, x64[::-1].copy()]), cfg["fs"], 2, 2, **kw).arrays
+    for i, w in enumerate((x64, x64[::-1].copy())):
+        try:
+            ref = orc.decode_all_candidates(w.astype(np.complex128), cfg["fs"], 2, 2, **kw)
+        except TypeError:
+            continue
+        assert int(b64.n_cand[i]) == len(ref)
+        for c, r in enumerate(ref):
+            assert (int(b64.cand_time[i, c]), int(b64.cand_freq[i, c]), bool(b64.ok[i, c]), int(b64.ldpc_errors[i, c]),
+                    bytes(b64.payload[i, c].numpy())) == (r["abs_time"], r["abs_freq"], r["ok"], r["ldpc_errors"], r["payload"])
+            assert abs(float(b64.cand_score[i, c]) - r["score"]) < SCORE_TOL
 
 
 @pytest.mark.parametrize("tag", ["k150_s4", "k38_s4"])

@@ -121,6 +121,18 @@ def test_exact_score_ties(orc, c1_slot, tag):
     check_traced(orc, c1_slot, 12000, gold, bins_per_tone=2, steps_per_symbol=2, **kw)
 
 
+@pytest.mark.parametrize("tag", ["c12000", "c12000_band", "c6000"])
+def test_complex_input(orc, tag):
+    """Complex baseband into decode_ft8_message (the reference keeps the f >= 0 rows of its two-sided spectrogram,
+    ft8_decode.py:316-325; src/tests/pluto-sdr/receive.py calls it that way): traced reference runs, tests/golden/cplx.npz."""
+    import hashlib
+    g = load_golden("cplx.npz")
+    cfg, kw = json.loads(str(g[tag + "__cfg"])), json.loads(str(g[tag + "__kw"]))
+    x = synth.c4_capture(**cfg)
+    assert x.dtype == np.complex128 and hashlib.sha256(np.ascontiguousarray(x).tobytes()).hexdigest() == str(g[tag + "__input_sha256"])
+    check_traced(orc, x, cfg["fs"], golden_case(g, tag), bins_per_tone=2, steps_per_symbol=2, **kw)
+
+
 def test_wav_fixture(orc):
     g = load_golden("wav_fs20k.npz")
     x = (g["samples_int16"].astype(np.float32) / 32767).astype(np.float64)

@@ -63,13 +63,21 @@ def draw_trial(rng):
         waves[i] = sig + rng.standard_normal(n) * float(rng.choice([0.0, 0.3, 1.0, 1.0]))
     chunk = int(rng.choice([0, 0, 1, 2, 3]))
     # input type and placement: what the GPU gets (`given`) and the float64 values it stands for (`waves`, the oracle's input)
-    kind = str(rng.choice(["f32", "f32", "f64", "pcm16", "f32_pinned", "f32_device", "f64_device"]))
+    kind = str(rng.choice(["f32", "f32", "f64", "pcm16", "f32_pinned", "f32_device", "f64_device", "c128", "c64", "c128_device"]))
     extra = {}
     if kind == "pcm16":
         pcm = np.clip(np.round(waves / max(1e-9, np.abs(waves).max()) * 20000.0), -32768, 32767).astype(np.int16)
         given = pcm
         waves = (pcm.astype(np.float32) / np.float32(32767)).astype(np.float64)        # from_wave.py:62-66
         extra["pcm16"] = True
+    elif kind.startswith("c"):
+        # complex baseband: the real mix becomes its analytic-like counterpart (imaginary part: an independent draw)
+        waves = waves + 1j * (np.roll(waves, 7, axis=1) * 0.5 + rng.standard_normal(waves.shape) * 0.2)
+        if kind.startswith("c64"):
+            given = waves.astype(np.complex64)
+            waves = given.astype(np.complex128)
+        else:
+            given = waves
     elif kind.startswith("f64"):
         given = waves
     else:
