@@ -35,6 +35,7 @@ struct StftPlan {
     double scale = 0.0;         // 1/(sum win)^2
     int nthreads = 0;
     size_t smem = 0;
+    int big = 0;                // M does not fit shared memory: stft_db_big_kernel works in a global-memory scratch
     // canonical-geometry fast path (nperseg 1920, nfft 3840): extra twiddle tables for stft1920_kernel
     int fast = 0;
     double2 *tw2 = nullptr, *tw3 = nullptr, *logtab = nullptr;
@@ -276,6 +277,85 @@ __global__ void __launch_bounds__(BOUND, 1) stft_db_kernel(const StftArgs a) {
     }
 }
 
+// Frames too long for shared memory (M > 14 336 points: 96 kHz audio upwards, SDR baseband): the same Stockham
+// factorisation, out of place between two global-memory buffers of the CTA (L2-resident for moderate M), every output
+// of a pass summed directly from its r inputs (the index mapping of fft_pass_prime, for every radix: O(M r) per pass).
+// Generality over speed - this path exists so that no sample rate is refused; the reference's own SDR script runs
+// decode_ft8_message at 1 MHz (nfft = 320 000).
+constexpr int kBigThreads = 512;
+template <typename WaveT>
+__global__ void __launch_bounds__(kBigThreads) stft_db_big_kernel(const StftArgs a, double2 *scratch) {
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int M = a.M;
+    double2 *A = scratch + (size_t)blockIdx.x * 2 * (size_t)M, *B = A + M;
+    const int64_t n_items = a.n_slots * a.frames_out;
+    const int Fout = a.bin_hi - a.bin_lo;
+    for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int64_t slot = item / a.frames_out;
+        const int64_t fr = item - slot * a.frames_out;
+        const WaveT *x = reinterpret_cast<const WaveT *>(a.wave) + slot * a.slot_stride + (fr + a.frame_lo) * a.hop;
+        for (int n = tid; n < M; n += nthr) {
+            double2 v = make_double2(0.0, 0.0);
+            if (is_cplx<WaveT>::value) {
+                if (n < a.nperseg) {
+                    const double w = __ldg(&a.win[n]);
+                    const double2 c = load_cplx(x, n);
+                    v = make_double2(w * c.x, w * c.y);
+                }
+            } else if (a.even) {
+                const int i0 = 2 * n, i1 = 2 * n + 1;
+                if (i0 < a.nperseg) v.x = __ldg(&a.win[i0]) * load_sample(x, i0);
+                if (i1 < a.nperseg) v.y = __ldg(&a.win[i1]) * load_sample(x, i1);
+            } else if (n < a.nperseg) {
+                v.x = __ldg(&a.win[n]) * load_sample(x, n);
+            }
+            A[n] = v;
+        }
+        __syncthreads();
+        double2 *src = A, *dst = B;
+        int Ns = 1;
+        for (int p = 0; p < a.nrad; ++p) {
+            const int r = a.radix[p];
+            const int T = M / r, stepA = M / (Ns * r), stepB = M / r;
+            for (int o = tid; o < M; o += nthr) {
+                const int k = o % Ns;
+                const int t = (o / Ns) % r;
+                const int j = (o / (Ns * r)) * Ns + k;
+                int base = (int)(((int64_t)k * stepA + (int64_t)t * stepB) % M);
+                double2 acc = make_double2(0.0, 0.0);
+                int idx = 0;
+                for (int q = 0; q < r; ++q) {
+                    acc = cadd(acc, cmul(src[j + (int64_t)q * T], __ldg(&a.tw[idx])));
+                    idx += base;
+                    if (idx >= M) idx -= M;
+                }
+                dst[o] = acc;
+            }
+            __syncthreads();
+            double2 *tmp = src; src = dst; dst = tmp;
+            Ns *= r;
+        }
+        double *out = a.mag + (slot * a.frames_out + fr) * (int64_t)Fout;
+        for (int k = a.bin_lo + tid; k < a.bin_hi; k += nthr) {
+            double2 X;
+            if (a.even) {
+                const double2 z = src[k == M ? 0 : k];
+                const double2 zr = src[k == 0 ? 0 : M - k];
+                const double2 zc = make_double2(zr.x, -zr.y);
+                const double2 e = make_double2(0.5 * (z.x + zc.x), 0.5 * (z.y + zc.y));
+                const double2 o = csub(z, zc);
+                const double2 pw = cmul(__ldg(&a.twpost[k]), o);
+                X = make_double2(e.x + 0.5 * pw.y, e.y - 0.5 * pw.x);
+            } else {
+                X = src[k];
+            }
+            const double pwr = (X.x * X.x + X.y * X.y) * a.scale;
+            out[k - a.bin_lo] = 10.0 * log10(1e-12 + pwr);
+        }
+        __syncthreads();
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // Plan cache
 // ------------------------------------------------------------------------------------------
@@ -318,9 +398,14 @@ static int get_plan(int nperseg, int nfft, bool cplx, const StftPlan **out) {
     int max_smem = 0;
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     if ((int64_t)p.M > (int64_t)kMaxElemsPerThread * nthr || p.smem > (size_t)max_smem) {
-        set_error("nfft=%d needs a %d-point shared-memory FFT (%zu bytes); limit is %d points / %d bytes", nfft, p.M,
-                  p.smem, kMaxElemsPerThread * 1024, max_smem);
-        return FT8B_ERR_UNSUPPORTED;
+        // e.g. 96 kHz audio (M = 15 360) or SDR baseband: the frame does not fit a CTA's shared memory
+        if ((int64_t)p.M > (int64_t)1 << 24) {
+            set_error("nfft=%d needs a %d-point FFT per frame; the limit is %d points", nfft, p.M, 1 << 24);
+            return FT8B_ERR_UNSUPPORTED;
+        }
+        p.big = 1;
+        p.nthreads = 512;
+        p.smem = 0;
     }
     const long double two_pi = 6.283185307179586476925286766559L;
     std::vector<double2> tw(p.M), twp(p.M + 1);
@@ -488,6 +573,26 @@ int stft_db(const void *wave, int wave_dtype, int64_t n_slots, int64_t n_samples
     a.bin_lo = bin_lo; a.bin_hi = bin_hi; a.frame_lo = frame_lo; a.frames_out = frame_hi - frame_lo;
     a.mag = mag;
     const int64_t n_items = n_slots * a.frames_out;
+    if (plan->big) {
+        // scratch: two M-point buffers per CTA, stream-ordered allocation (the one path of the library that allocates per
+        // call: it is rare, and a cached buffer would have to be guarded against concurrent streams)
+        int64_t gridb = n_items < 2 * 148 ? n_items : 2 * 148;
+        while (gridb > 1 && (size_t)gridb * 2 * plan->M * sizeof(double2) > ((size_t)2 << 30)) gridb /= 2;   // <= 2 GiB
+        double2 *scratch = nullptr;
+        FT8B_CUDA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&scratch), (size_t)gridb * 2 * plan->M * sizeof(double2), stream));
+        switch (wave_dtype) {
+            case FT8B_DTYPE_C64: stft_db_big_kernel<float2><<<(unsigned)gridb, kBigThreads, 0, stream>>>(a, scratch); break;
+            case FT8B_DTYPE_C128: stft_db_big_kernel<double2><<<(unsigned)gridb, kBigThreads, 0, stream>>>(a, scratch); break;
+            case FT8B_DTYPE_I16: stft_db_big_kernel<short><<<(unsigned)gridb, kBigThreads, 0, stream>>>(a, scratch); break;
+            case FT8B_DTYPE_F32: stft_db_big_kernel<float><<<(unsigned)gridb, kBigThreads, 0, stream>>>(a, scratch); break;
+            default: stft_db_big_kernel<double><<<(unsigned)gridb, kBigThreads, 0, stream>>>(a, scratch); break;
+        }
+        const cudaError_t le = cudaGetLastError();
+        FT8B_CUDA_TRY(cudaFreeAsync(scratch, stream));
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        if (le != cudaSuccess) return cuda_fail(le, "stft_db_big_kernel");
+        return 0;
+    }
     int64_t grid = n_items;
     const int64_t cap = 148 * 64;  // persistent-ish: many CTAs per SM, grid-stride over frames
     if (grid > cap) grid = cap;

@@ -583,8 +583,8 @@ def test_edge_cases():
     assert len(b) == 0
     with pytest.raises(NotImplementedError):
         fd.decode_slots(np.zeros((1, 180000), dtype=np.float32), 12000, max_candidates=5000)
-    with pytest.raises(NotImplementedError):
-        sa.calculate_spectrogram(np.zeros(400000), 1_000_000)               # nfft 320000: beyond the smem FFT
+    S, f, t = sa.calculate_spectrogram(np.zeros(400000), 1_000_000)         # nfft 320000: the global-memory FFT path
+    assert S.shape == (320000, 4) and np.all(S == S[0, 0]) and abs(S[0, 0] + 120.0) < 1e-9
     # constant spectrogram with min_score <= 0: every score ties at 0.0 (the reference raises TypeError);
     # the deterministic tie-break returns the first K positions in scan order
     wf = fd.create_waterfall_from_spectrogram(np.zeros((120, 160)), 2, 2)
@@ -1172,6 +1172,46 @@ def test_drift_sync_vs_cpu_statement(orc, F, T, s, b, hyps):
         fin = np.isfinite(ref)
         assert np.abs(g[fin] - ref[fin]).max() < 1e-12
         assert (h != ref_h).mean() < 1e-3          # another winner only between hypotheses that tie to rounding
+
+
+@pytest.mark.parametrize("fs,b,s,kind", [(96000, 2, 2, "f32"), (192000, 2, 2, "f64"), (250000, 1, 2, "c128"), (44100, 5, 3, "f32")])
+def test_high_sample_rates_beyond_the_smem_fft(orc, fs, b, s, kind):
+    """Frames of more than 14 336 transform points (96 kHz audio upwards, SDR baseband) run on stft_db_big_kernel (global-
+    memory Stockham): spectrogram against NumPy, the whole decode against the oracle record by record."""
+    rng = np.random.default_rng(fs + b)
+    dur = 14.0
+    n = int(fs * dur)
+    pl = bytes(rng.integers(0, 256, 9, dtype=np.uint8)) + bytes([int(rng.integers(0, 32)) << 3])
+    burst = synth.ft8_generator(pl, fs, 1234.5)
+    x = rng.standard_normal(n) * 0.7
+    x[int(0.4 * fs):int(0.4 * fs) + len(burst)] += burst
+    if kind == "c128":
+        bb = synth.ft8_baseband(np.frombuffer(pl, dtype=np.uint8), fs, 1234.5)
+        x = (rng.standard_normal(n) + 1j * rng.standard_normal(n)) * 0.5
+        x[int(0.4 * fs):int(0.4 * fs) + len(bb)] += bb
+    elif kind == "f32":
+        x = x.astype(np.float32)
+    nperseg, hop, nfft = fd._lib.plan(fs, b, s)
+    assert (nfft if kind == "c128" else nfft // 2) > 14336
+    # spectrogram (first frames) against a NumPy restatement of the scipy call
+    m = nperseg + 3 * hop
+    S, f, t = sa.calculate_spectrogram(x[:m], fs, b, s)
+    win = 0.5 - 0.5 * np.cos(2 * np.pi * np.arange(nperseg) / nperseg)
+    xw = x[:m].astype(np.complex128 if kind == "c128" else np.float64)
+    frames = np.stack([xw[j * hop:j * hop + nperseg] * win for j in range(4)])
+    ref = np.fft.fftshift(10 * np.log10(1e-12 + np.abs(np.fft.fft(frames, n=nfft, axis=1)) ** 2 / win.sum() ** 2).T, axes=0)
+    assert S.shape == ref.shape and np.abs(S - ref).max() < (1e-4 if kind == "f32" else 1e-8)
+    # decode in a band around the burst (keeps the oracle's score map small) against the oracle
+    kw = dict(max_candidates=30, min_score=5.0, max_iterations=20, freq_min=900.0, freq_max=1700.0)
+    ref = orc.decode_all_candidates(x.astype(np.complex128 if kind == "c128" else np.float64), fs, b, s, **kw)
+    a = fd.decode_slots(x.reshape(1, -1), fs, b, s, **kw).arrays
+    assert int(a.n_cand[0]) == len(ref) and len(ref) > 0
+    for c, r in enumerate(ref):
+        assert (int(a.cand_time[0, c]), int(a.cand_freq[0, c]), bool(a.ok[0, c]), int(a.ldpc_errors[0, c]),
+                bytes(a.payload[0, c].numpy())) == (r["abs_time"], r["abs_freq"], r["ok"], r["ldpc_errors"], r["payload"])
+        assert abs(float(a.cand_score[0, c]) - r["score"]) < SCORE_TOL
+    if fs != 44100:                         # (osr 5x3 at 44.1 kHz: the oracle does not recover the burst either)
+        assert any(r["ok"] and r["payload"] == pl for r in ref)
 
 
 def test_long_capture_beyond_the_walk_kernels(orc):
