@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("FT8B_LIB_PATH") or os.path.join(_HERE, "libft8b200.so
 ERR_ARG, ERR_UNSUPPORTED, ERR_NO_DEVICE = -1, -2, -3
 DTYPE_F32, DTYPE_F64, DTYPE_I16, DTYPE_C64, DTYPE_C128 = 0, 1, 2, 3, 4
 DRIFT_AUTO, DRIFT_WALK, DRIFT_BLOCKSUM, DRIFT_DIRECT = 0, 1, 2, 3
-MAX_CANDIDATES = 4096
+MAX_CANDIDATES = 1048576          # FT8B_MAX_CANDIDATES (strict top-K: 4096)
 FLAG_STRICT_TOPK = 1
 LDPC_N = 174
 

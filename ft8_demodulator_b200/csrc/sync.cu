@@ -273,7 +273,11 @@ struct SelArgs {
     // list, threshold tests of scores within kSelTol of min_score, and the record replacement.
     const double *mag;      // [n_slots][T][F]
     int T, F, s, b, nb;
+    // lists too long for shared memory (K > kSelSmemK): [n_slots][Kpad] scores / scan indices in global memory, else null
+    double *big_s;
+    long long *big_i;
 };
+constexpr int kSelSmemK = 4096;     // longest list the selection keeps in shared memory (64 KB)
 
 // The sync kernels add per cell, then per Costas block, then per score (what lets neighbouring candidates share work);
 // the reference keeps ONE running sum.  The two agree to ~1e-13 relative, not bit for bit.
@@ -436,8 +440,10 @@ template <int THREADS>
 __global__ void __launch_bounds__(THREADS) select_candidates_kernel(const SelArgs a) {
     constexpr int kSelThreads = THREADS, kSelWarps = THREADS / 32;
     extern __shared__ unsigned char sel_smem[];
-    double *hs = reinterpret_cast<double *>(sel_smem);                   // [Kpad] scores
-    long long *hi = reinterpret_cast<long long *>(hs + a.Kpad);          // [Kpad] scan indices
+    const int64_t slot = blockIdx.x;
+    // [Kpad] scores and scan indices: shared memory, or (K > kSelSmemK) this slot's rows of the global scratch
+    double *hs = a.big_s ? a.big_s + slot * a.Kpad : reinterpret_cast<double *>(sel_smem);
+    long long *hi = a.big_i ? a.big_i + slot * a.Kpad : reinterpret_cast<long long *>(reinterpret_cast<double *>(sel_smem) + a.Kpad);
     __shared__ int warp_cnt[32];
     __shared__ int s_base, s_done;
     __shared__ long long s_cut;
@@ -450,7 +456,6 @@ __global__ void __launch_bounds__(THREADS) select_candidates_kernel(const SelArg
     __shared__ long long s_ev_i;
     __shared__ int s_replaced;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int64_t slot = blockIdx.x;
     const double *sc = a.scores + slot * a.L;
     const double *mag = a.mag ? a.mag + slot * (int64_t)a.T * a.F : nullptr;
     const int K = a.K;
@@ -635,8 +640,11 @@ __global__ void __launch_bounds__(THREADS) select_candidates_kernel(const SelArg
     }
     __syncthreads();
 
-    // ---- phase C: sort H by (score desc, scan index asc) - bitonic over Kpad ----
-    sel_bitonic<THREADS, false>(hs, hi, a.Kpad, tid);
+    // ---- phase C: sort H by (score desc, scan index asc) - bitonic over the occupied power-of-two prefix
+    // (entries n_first .. Kpad-1 are padding: -inf, largest index)
+    int P = 2;
+    while (P < n_first) P <<= 1;
+    sel_bitonic<THREADS, false>(hs, hi, P, tid);
     // ---- phase D (rare): exact ties in the list come out in the reference's heap-array order ----
     int tie = 0;
     for (int i = tid; i + 1 < n_first; i += kSelThreads) tie |= (hs[i] == hs[i + 1]) ? 1 : 0;
@@ -646,7 +654,7 @@ __global__ void __launch_bounds__(THREADS) select_candidates_kernel(const SelArg
             for (int i = tid; i < n_first; i += kSelThreads)
                 if (hi[i] == s_rec_i) { hs[i] = s_ev_s; hi[i] = s_ev_i; }
         __syncthreads();
-        sel_bitonic<THREADS, true>(hs, hi, a.Kpad, tid);    // push order
+        sel_bitonic<THREADS, true>(hs, hi, P, tid);         // push order
         if (tid == 0) {
             if (sel_heap_replay(hs, hi, n_first, replaced, s_rec_s, s_rec_i)) {
                 for (int i = 0; i < n_first; ++i) hi[i] |= (long long)i << kSelTagShift;
@@ -659,7 +667,7 @@ __global__ void __launch_bounds__(THREADS) select_candidates_kernel(const SelArg
             }
         }
         __syncthreads();
-        sel_bitonic<THREADS, false>(hs, hi, a.Kpad, tid);
+        sel_bitonic<THREADS, false>(hs, hi, P, tid);
     }
     for (int i = tid; i < K; i += kSelThreads) {
         const int64_t o = slot * K + i;
@@ -994,8 +1002,8 @@ int select_candidates(const double *scores, int64_t n_slots, int nt, int nf, int
                       cudaStream_t stream) {
     if (tiles && n_pass) FT8B_ARG_FAIL("select_candidates: n_pass needs the full scan (no strip summaries)");
     if (!cand_time || !cand_freq || !cand_score || !n_cand) FT8B_ARG_FAIL("ft8b_select_candidates: null pointer");
-    if (K < 0 || K > FT8B_MAX_CANDIDATES) {
-        set_error("ft8b_select_candidates: K=%d outside [0,%d]", K, FT8B_MAX_CANDIDATES);
+    if (K < 0 || K > FT8B_MAX_CANDIDATES || (n_tiles < 0 && K > kSelSmemK)) {
+        set_error("ft8b_select_candidates: K=%d outside [0,%d]", K, n_tiles < 0 ? kSelSmemK : FT8B_MAX_CANDIDATES);
         return FT8B_ERR_UNSUPPORTED;
     }
     if (n_slots <= 0) return 0;
@@ -1018,6 +1026,22 @@ int select_candidates(const double *scores, int64_t n_slots, int nt, int nf, int
         int t0c, ntc, nfc;
         ft8b_search_ranges(T, F, s, b, &t0c, &ntc, &nfc);
         if (t0c != t0 || ntc != nt || nfc != nf) FT8B_ARG_FAIL("select_candidates: score map does not belong to this spectrogram geometry");
+    }
+    a.big_s = nullptr; a.big_i = nullptr;
+    if (K > kSelSmemK) {
+        // a list this long (the reference takes any max_candidates; callers pass huge values for "no limit") lives in a
+        // stream-ordered global scratch: same kernel, its two arrays just point there
+        void *scratch = nullptr;
+        const size_t bytes = (size_t)n_slots * kp * (sizeof(double) + sizeof(long long));
+        FT8B_CUDA_TRY(cudaMallocAsync(&scratch, bytes, stream));
+        a.big_s = reinterpret_cast<double *>(scratch);
+        a.big_i = reinterpret_cast<long long *>(a.big_s + (size_t)n_slots * kp);
+        select_candidates_kernel<1024><<<(unsigned)n_slots, 1024, 0, stream>>>(a);
+        const cudaError_t le = cudaGetLastError();
+        FT8B_CUDA_TRY(cudaFreeAsync(scratch, stream));
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        if (le != cudaSuccess) return cuda_fail(le, "select_candidates_kernel");
+        return 0;
     }
     const size_t smem = (size_t)kp * (sizeof(double) + sizeof(long long));
     if (n_tiles < 0) {       // strict top-K (opt-in extension)

@@ -55,7 +55,8 @@ extern "C" {
 #define FT8B_LDPC_N 174
 #define FT8B_LDPC_M 83
 #define FT8B_FLAG_STRICT_TOPK 1    /* ft8b_decode_params.flags: candidate list = the K best scores (ft8b_select_topk) */
-#define FT8B_MAX_CANDIDATES 4096   /* K limit of ft8b_select_candidates */
+#define FT8B_MAX_CANDIDATES 1048576   /* K limit of the selection (lists above 4096 entries live in a global scratch);
+                                         ft8b_select_topk / FT8B_FLAG_STRICT_TOPK: 4096 */
 
 int ft8b_version(void);
 const char *ft8b_last_error(void);

@@ -582,7 +582,9 @@ def test_edge_cases():
     b = fd.decode_slots(np.zeros((0, 180000), dtype=np.float32), 12000)
     assert len(b) == 0
     with pytest.raises(NotImplementedError):
-        fd.decode_slots(np.zeros((1, 180000), dtype=np.float32), 12000, max_candidates=5000)
+        fd.decode_slots(np.zeros((1, 180000), dtype=np.float32), 12000, max_candidates=5000, strict_topk=True)
+    with pytest.raises(NotImplementedError):
+        fd.decode_slots(np.zeros((1, 180000), dtype=np.float32), 12000, max_candidates=2_000_000)
     S, f, t = sa.calculate_spectrogram(np.zeros(400000), 1_000_000)         # nfft 320000: the global-memory FFT path
     assert S.shape == (320000, 4) and np.all(S == S[0, 0]) and abs(S[0, 0] + 120.0) < 1e-9
     # constant spectrogram with min_score <= 0: every score ties at 0.0 (the reference raises TypeError);
@@ -1212,6 +1214,32 @@ def test_high_sample_rates_beyond_the_smem_fft(orc, fs, b, s, kind):
         assert abs(float(a.cand_score[0, c]) - r["score"]) < SCORE_TOL
     if fs != 44100:                         # (osr 5x3 at 44.1 kHz: the oracle does not recover the burst either)
         assert any(r["ok"] and r["payload"] == pl for r in ref)
+
+
+@pytest.mark.parametrize("K,thr", [(5000, 2.0), (70000, 0.5)])
+def test_candidate_lists_beyond_shared_memory(orc, K, thr):
+    """max_candidates above 4096 (the reference takes any value; callers pass huge ones for "no limit"): the list lives in
+    a global scratch instead of shared memory - fewer passers than K, more passers than K (record replacement), and the
+    whole decode of two slots against the oracle."""
+    slot = synth.c2_slot()[0].astype(np.float32)
+    waves = np.stack([slot, slot[::-1].copy()])
+    kw = dict(max_candidates=K, min_score=thr, max_iterations=3, freq_max=3100)
+    a = fd.decode_slots(waves, 12000, 2, 2, **kw).arrays
+    compared = 0
+    for i in range(2):
+        try:
+            ref = orc.decode_all_candidates(waves[i].astype(np.float64), 12000, 2, 2, **kw)
+        except TypeError:
+            continue                            # the reference's heapq compares an exact tie in this slot and raises
+        compared += 1
+        assert int(a.n_cand[i]) == len(ref) and len(ref) > 4096
+        got = list(zip(a.cand_time[i, :len(ref)].tolist(), a.cand_freq[i, :len(ref)].tolist()))
+        assert got == [(r["abs_time"], r["abs_freq"]) for r in ref]
+        assert np.abs(a.cand_score[i, :len(ref)].numpy() - np.array([r["score"] for r in ref])).max() < SCORE_TOL
+        assert a.ok[i, :len(ref)].tolist() == [int(r["ok"]) for r in ref]
+        assert a.ldpc_errors[i, :len(ref)].tolist() == [r["ldpc_errors"] for r in ref]
+        assert [bytes(p) for p in a.payload[i, :len(ref)].numpy()] == [r["payload"] for r in ref]
+    assert compared >= 1
 
 
 def test_long_capture_beyond_the_walk_kernels(orc):
