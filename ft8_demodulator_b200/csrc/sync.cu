@@ -436,14 +436,16 @@ constexpr long long kSelIdxMask = (1LL << kSelTagShift) - 1;
 // THREADS: 256 for short lists (K <= 64: four CTAs per SM hide each other's barrier and DRAM latencies - 0.235 ms per
 // 4096 slots at K = 20 against 0.47 ms with one 1024-thread CTA per SM), 1024 for long ones (the sort and the
 // compaction of thousands of candidates want the threads).
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS) select_candidates_kernel(const SelArgs a) {
+// BIG: the list lives in the global scratch (K > kSelSmemK); a compile-time switch, so that the common case keeps plain
+// shared-memory accesses (generic pointers here cost 0.03 ms per 4096 slots)
+template <int THREADS, bool BIG = false>
+__global__ void __launch_bounds__(THREADS, THREADS <= 256 ? 5 : 1) select_candidates_kernel(const SelArgs a) {   // 5 x 256 threads per SM: 48 registers
     constexpr int kSelThreads = THREADS, kSelWarps = THREADS / 32;
     extern __shared__ unsigned char sel_smem[];
     const int64_t slot = blockIdx.x;
     // [Kpad] scores and scan indices: shared memory, or (K > kSelSmemK) this slot's rows of the global scratch
-    double *hs = a.big_s ? a.big_s + slot * a.Kpad : reinterpret_cast<double *>(sel_smem);
-    long long *hi = a.big_i ? a.big_i + slot * a.Kpad : reinterpret_cast<long long *>(reinterpret_cast<double *>(sel_smem) + a.Kpad);
+    double *hs = BIG ? a.big_s + slot * a.Kpad : reinterpret_cast<double *>(sel_smem);
+    long long *hi = BIG ? a.big_i + slot * a.Kpad : reinterpret_cast<long long *>(reinterpret_cast<double *>(sel_smem) + a.Kpad);
     __shared__ int warp_cnt[32];
     __shared__ int s_base, s_done;
     __shared__ long long s_cut;
@@ -1036,7 +1038,7 @@ int select_candidates(const double *scores, int64_t n_slots, int nt, int nf, int
         FT8B_CUDA_TRY(cudaMallocAsync(&scratch, bytes, stream));
         a.big_s = reinterpret_cast<double *>(scratch);
         a.big_i = reinterpret_cast<long long *>(a.big_s + (size_t)n_slots * kp);
-        select_candidates_kernel<1024><<<(unsigned)n_slots, 1024, 0, stream>>>(a);
+        select_candidates_kernel<1024, true><<<(unsigned)n_slots, 1024, 0, stream>>>(a);
         const cudaError_t le = cudaGetLastError();
         FT8B_CUDA_TRY(cudaFreeAsync(scratch, stream));
         g_launches.fetch_add(1, std::memory_order_relaxed);
