@@ -20,7 +20,7 @@ import ft8_oracle as orc  # noqa: E402
 from ft8_demodulator_b200 import synth  # noqa: E402
 from ft8_demodulator_b200.ft8_demodulator import ft8_decode as fd  # noqa: E402
 
-RATES = [12000, 12000, 12000, 6000, 8000, 10000, 3500, 4500, 16000, 20000, 24000, 11025, 22050, 44100, 48000, 7350]
+RATES = [12000, 12000, 12000, 6000, 8000, 10000, 3500, 4500, 16000, 20000, 24000, 11025, 22050, 44100, 48000, 7350, 96000]
 
 
 def draw_trial(rng):
@@ -30,7 +30,7 @@ def draw_trial(rng):
     dur = float(rng.choice([10.0, 12.7, 13.0, 14.0, 15.0, 15.0, 15.0, 16.5, 30.0, 47.0]))
     n = int(fs * dur) + int(rng.integers(0, 7))
     B = int(rng.integers(1, 6))
-    kw = dict(max_candidates=int(rng.choice([1, 2, 5, 20, 20, 64, 65, 150])),
+    kw = dict(max_candidates=int(rng.choice([1, 2, 5, 20, 20, 64, 65, 150, 5000])),
               min_score=float(rng.choice([-3.0, 0.0, 1.0, 1.0, 2.5, 6.0, 10.0])),
               max_iterations=int(rng.choice([0, 1, 5, 20, 20, 40])))
     masks = {}
@@ -95,26 +95,41 @@ def draw_trial(rng):
 
 
 def compare(batch, ref_lists):
+    """None when every record equals the oracle's; "near-tie: ..." when the only difference is the ORDER of candidates
+    whose scores agree to 1e-9 (two different FFT factorisations round the spectrogram differently at ~1e-14 dB, so a
+    score that cancels to exactly 0.0 in the oracle can be 5e-16 here - constant or silent audio does that; the
+    documented spectrogram tolerance, not a selection error); anything else is a failure."""
     a = batch.arrays
+    near = None
     for i, ref in enumerate(ref_lists):
         if ref is None:
             continue
         if int(a.n_cand[i]) != len(ref):
             return "slot %d: n_cand %d vs %d" % (i, int(a.n_cand[i]), len(ref))
-        for c, r in enumerate(ref):
-            got = (int(a.cand_time[i, c]), int(a.cand_freq[i, c]), bool(a.ok[i, c]), int(a.ldpc_errors[i, c]),
-                   int(a.crc_extracted[i, c]), int(a.crc_calculated[i, c]), bytes(a.payload[i, c].numpy()))
-            want = (r["abs_time"], r["abs_freq"], r["ok"], r["ldpc_errors"], r["crc_extracted"], r["crc_calculated"], r["payload"])
-            if got != want:
-                return "slot %d cand %d: %r vs %r" % (i, c, got, want)
-            if not abs(float(a.cand_score[i, c]) - r["score"]) < 1e-9:
-                return "slot %d cand %d: score %r vs %r" % (i, c, float(a.cand_score[i, c]), r["score"])
-    return None
+        got = [(int(a.cand_time[i, c]), int(a.cand_freq[i, c]), bool(a.ok[i, c]), int(a.ldpc_errors[i, c]),
+                int(a.crc_extracted[i, c]), int(a.crc_calculated[i, c]), bytes(a.payload[i, c].numpy())) for c in range(len(ref))]
+        want = [(r["abs_time"], r["abs_freq"], r["ok"], r["ldpc_errors"], r["crc_extracted"], r["crc_calculated"], r["payload"])
+                for r in ref]
+        gs = [float(a.cand_score[i, c]) for c in range(len(ref))]
+        ws = [r["score"] for r in ref]
+        if any(not abs(x - y) < 1e-9 for x, y in zip(gs, ws)):
+            c = next(c for c in range(len(ref)) if not abs(gs[c] - ws[c]) < 1e-9)
+            return "slot %d cand %d: score %r vs %r" % (i, c, gs[c], ws[c])
+        if got == want:
+            continue
+        c = next(c for c in range(len(ref)) if got[c] != want[c])
+        own = {w[:2]: (w, sc) for w, sc in zip(want, ws)}
+        same_records = sorted(got) == sorted(want) and all(abs(own[g[:2]][1] - sc) < 1e-9 for g, sc in zip(got, gs))
+        if not same_records:
+            return "slot %d cand %d: %r vs %r" % (i, c, got[c], want[c])
+        near = "near-tie: slot %d from cand %d on, same records, order differs among scores equal to 1e-9 (%r vs %r)" % (
+            i, c, got[c][:2], want[c][:2])
+    return near
 
 
 def run(trials, seed):
     rng = np.random.default_rng(seed)
-    failures, skipped, records, decoded = [], 0, 0, 0
+    failures, near_ties, skipped, records, decoded = [], [], 0, 0, 0
     t0 = time.time()
     for t in range(trials):
         fs, b, s, waves, kw, masks, chunk, given, kind, extra = draw_trial(rng)
@@ -144,10 +159,12 @@ def run(trials, seed):
         why = compare(batch, ref)
         records += sum(len(r) for r in ref if r is not None)
         decoded += sum(1 for r in ref if r is not None for c in r if c["ok"])
-        if why:
+        if why and why.startswith("near-tie"):
+            near_ties.append(dict(desc, why=why))
+        elif why:
             failures.append(dict(desc, why=why))
     return dict(tool="fuzz_parity", trials=trials, seed=seed, skipped=skipped, candidate_records_compared=records,
-                decodes_among_them=decoded, failures=failures, seconds=round(time.time() - t0, 1))
+                decodes_among_them=decoded, near_tie_reorders=near_ties, failures=failures, seconds=round(time.time() - t0, 1))
 
 
 def main():
