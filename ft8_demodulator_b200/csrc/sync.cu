@@ -436,10 +436,13 @@ constexpr long long kSelIdxMask = (1LL << kSelTagShift) - 1;
 // THREADS: 256 for short lists (K <= 64: four CTAs per SM hide each other's barrier and DRAM latencies - 0.235 ms per
 // 4096 slots at K = 20 against 0.47 ms with one 1024-thread CTA per SM), 1024 for long ones (the sort and the
 // compaction of thousands of candidates want the threads).
+#ifndef FT8B_SEL_MINB
+#define FT8B_SEL_MINB 5
+#endif
 // BIG: the list lives in the global scratch (K > kSelSmemK); a compile-time switch, so that the common case keeps plain
 // shared-memory accesses (generic pointers here cost 0.03 ms per 4096 slots)
 template <int THREADS, bool BIG = false>
-__global__ void __launch_bounds__(THREADS, THREADS <= 256 ? 5 : 1) select_candidates_kernel(const SelArgs a) {   // 5 x 256 threads per SM: 48 registers
+__global__ void __launch_bounds__(THREADS, THREADS <= 256 ? FT8B_SEL_MINB : 1) select_candidates_kernel(const SelArgs a) {   // 5 x 256 threads per SM: 48 registers
     constexpr int kSelThreads = THREADS, kSelWarps = THREADS / 32;
     extern __shared__ unsigned char sel_smem[];
     const int64_t slot = blockIdx.x;
