@@ -51,7 +51,7 @@ def run(trials, seed):
     t0 = time.time()
     for t in range(trials):
         mag, tosr, fosr, kind = draw_mag(rng)
-        K = int(rng.choice([1, 3, 20, 64, 65, 300]))
+        K = int(rng.choice([1, 3, 20, 64, 65, 300, 5000]))
         thr = float(rng.choice([-5.0, 0.0, 0.5, 2.0, 6.0]))
         desc = dict(trial=t, shape=list(mag.shape), tosr=tosr, fosr=fosr, kind=kind, K=K, thr=thr)
         wf = fd.create_waterfall_from_spectrogram(mag, tosr, fosr)
