@@ -10,7 +10,7 @@ rows = list(csv.reader(open(raw)))
 hdr, units, data = rows[0], rows[1], rows[2:]
 ix = {h: i for i, h in enumerate(hdr)}
 names = {"stft1920": "stft_db", "stft_db_kernel": "stft_db", "sync_scores": "costas_sync", "select_candidates": "select",
-         "decode_kernel": "decode"}
+         "llr_kernel": "llr", "decode_kernel": "decode"}
 
 
 def to_bytes(v, unit):
@@ -24,8 +24,8 @@ for r in data:
     k = next((v for n, v in names.items() if n in r[ix["Kernel Name"]]), None)
     if not k:
         continue
-    if k == "decode":                # first decode_kernel launch of a step extracts LLRs, the second runs BP + CRC
-        k = "llr" if n_decode == 0 else "ldpc_crc"
+    if k == "decode":                # BP + CRC (captures made before llr_kernel existed: the first decode_kernel launch
+        k = "ldpc_crc" if ("llr" in res or n_decode > 0) else "llr"      # of a step extracted the LLRs)
         n_decode += 1
         if k in res:
             continue

@@ -54,7 +54,7 @@ for r in rows[1:]:
 tot = sum(a[1] for a in agg.values())
 plain = last_json_line(os.path.join(G, tag + "_bench_plain.log"))
 with open(os.path.join(P, rnd + "_ncu_launches_summary.txt"), "w") as f:
-    f.write("ncu --metrics gpu__time_duration.sum --clock-control none -k regex:stft|sync_scores|select_candidates|decode_kernel -c 400\n")
+    f.write("ncu --metrics gpu__time_duration.sum --clock-control none -k regex:stft|sync_scores|select_candidates|llr_kernel|decode_kernel -c 400\n")
     f.write("    python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu      (%d slots; first 400 launches)\n" % plain["config"]["slots_per_gpu"])
     f.write("per-launch times under ncu are cold-cache and serialised: compare SHARES with bench.py's `stages[*].share`\n\n")
     f.write("%-40s %8s %12s %8s\n" % ("kernel", "launches", "total ms", "share"))
@@ -72,10 +72,10 @@ subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_traffic.py"), r
 srcp = os.path.join(G, tag + "_src_all.csv")
 subprocess.run("ncu -i %s --page source --csv > %s 2>/dev/null" % (rep, srcp), shell=True, check=True)
 out = open(os.path.join(P, rnd + "_ncu_full_256slots.txt"), "w")
-out.write("ncu --set full --clock-control none --import-source on -k regex:stft1920|sync_scores|decode_kernel|select_cand -s 5 -c 5 python tools/profile_step.py 256 2\n")
-out.write("(one decode step over 256 slots: stft1920 -> sync_scores -> select -> decode_kernel[LLR] -> decode_kernel[BP])\n\n")
+out.write("ncu --set full --clock-control none --import-source on -k regex:stft1920|sync_scores|llr_kernel|decode_kernel|select_cand -s 5 -c 5 python tools/profile_step.py 256 2\n")
+out.write("(one decode step over 256 slots: stft1920 -> sync_scores -> select -> llr_kernel -> decode_kernel[BP])\n\n")
 out.write(subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_metrics.py"), raw], capture_output=True, text=True).stdout)
-names = ["stft1920", "sync_scores", "select_candidates", "decode_kernel (LLR launch)", "decode_kernel (BP launch)"]
+names = ["stft1920", "sync_scores", "select_candidates", "llr_kernel", "decode_kernel (BP launch)"]
 for sec, name in enumerate(names):
     out.write("\n== SASS mix / stall reasons: %s\n" % name)
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_sass_summary.py"), srcp, str(2 * sec)], capture_output=True, text=True)
