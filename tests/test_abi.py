@@ -117,7 +117,7 @@ def test_host_entry_argument_checks():
     assert L.ft8b_decode_slots_host(x.ctypes.data, _lib.DTYPE_F32, 1, 180000, 100, C.byref(prm), -1, 0, *ptrs) == _lib.ERR_ARG  # stride < n
     assert L.ft8b_decode_slots_host(None, _lib.DTYPE_F32, 1, 180000, 180000, C.byref(prm), -1, 0, *ptrs) == _lib.ERR_ARG
     assert L.ft8b_decode_slots_host(x.ctypes.data, _lib.DTYPE_F32, 1, 180000, 180000, C.byref(prm), -1, 0, *(ptrs[:8] + [None])) == _lib.ERR_ARG
-    big = engine.make_params(12000, 2, 2, 5000, 1, 20, 0, 1920, 0, 186)
+    big = engine.make_params(12000, 2, 2, 2_000_000, 1, 20, 0, 1920, 0, 186)      # above FT8B_MAX_CANDIDATES (2^20)
     assert L.ft8b_decode_slots_host(x.ctypes.data, _lib.DTYPE_F32, 1, 180000, 180000, C.byref(big), -1, 0, *ptrs) == _lib.ERR_UNSUPPORTED
     assert L.ft8b_decode_slots_host(x.ctypes.data, _lib.DTYPE_F32, 0, 180000, 180000, C.byref(prm), -1, 0, *ptrs) == 0       # empty batch
 
