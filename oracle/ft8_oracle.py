@@ -99,14 +99,17 @@ def plan(sample_rate, bins_per_tone=2, steps_per_symbol=2):
 
 
 def spectrogram_pos(wave, sample_rate, bins_per_tone=2, steps_per_symbol=2):
-    """dB spectrogram rows f >= 0, shape [ceil(nfft/2), T] (what ft8_decode.py:323-325 keeps)."""
-    x = _f64(wave)
+    """dB spectrogram rows f >= 0, shape [ceil(nfft/2), T] (what ft8_decode.py:323-325 keeps); real or complex audio."""
+    cplx = np.iscomplexobj(wave)
+    x = np.ascontiguousarray(np.asarray(wave, dtype=np.complex128).reshape(-1)).view(np.float64) if cplx else _f64(wave)
+    n = len(x) // 2 if cplx else len(x)
     nperseg, hop, nfft = plan(sample_rate, bins_per_tone, steps_per_symbol)
-    T = lib().orc_num_frames(len(x), nperseg, hop)
+    T = lib().orc_num_frames(n, nperseg, hop)
     if T <= 0:
         return np.zeros((0, 0))
     mag = np.empty(((nfft + 1) // 2, T), dtype=np.float64)
-    rc = lib().orc_spectrogram_pos(_dp(x), len(x), nperseg, hop, nfft, _dp(mag))
+    fn = lib().orc_spectrogram_pos_c if cplx else lib().orc_spectrogram_pos
+    rc = fn(_dp(x), n, nperseg, hop, nfft, _dp(mag))
     if rc:
         raise ValueError("orc_spectrogram_pos failed: %d" % rc)
     return mag

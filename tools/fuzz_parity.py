@@ -94,9 +94,29 @@ def draw_trial(rng):
     return fs, b, s, waves, kw, masks, chunk, given, kind, extra
 
 
-def compare(batch, ref_lists):
-    """None when every record equals the oracle's; "near-tie: ..." when the only difference is the ORDER of candidates
-    whose scores agree to 1e-9 (two different FFT factorisations round the spectrogram differently at ~1e-14 dB, so a
+def rerun_on_oracle_spectrogram(ctx, slot, want):
+    """The GPU's ft8_decode_candidate on the oracle's (masked) spectrogram of this slot == the oracle's record?"""
+    from ft8_demodulator_b200.ft8_demodulator.ftx_types import FT8Candidate
+    fs, b, s, waves, kw, masks = ctx
+    key = ("wf", slot)
+    if key not in ctx_cache:
+        ctx_cache.clear()
+        mag = orc.spectrogram_pos(waves[slot], fs, b, s)
+        nperseg, hop, nfft = orc.plan(fs, b, s)
+        klo, khi, jlo, jhi = orc.masks(fs, nperseg, hop, nfft, mag.shape[1], masks.get("freq_min"), masks.get("freq_max"),
+                                       masks.get("time_min"), masks.get("time_max"))
+        ctx_cache[key] = fd.create_waterfall_from_spectrogram(np.ascontiguousarray(mag[klo:khi, jlo:jhi]), s, b)
+    wf = ctx_cache[key]
+    ok, msg, st = fd.ft8_decode_candidate(wf, FT8Candidate(waterfall=wf, abs_time=want[0], abs_freq=want[1]), kw["max_iterations"])
+    return (bool(ok), st.ldpc_errors, st.crc_extracted, st.crc_calculated, bytes(msg.payload)) == tuple(want[2:])
+
+
+ctx_cache = {}
+
+
+def compare(batch, ref_lists, ctx=None):
+    """None when every record equals the oracle's; a "near-tie: ..." / "spectrogram-rounding: ..." note when the only
+    difference is the ORDER of candidates whose scores agree to 1e-9 (two different FFT factorisations round the spectrogram differently at ~1e-14 dB, so a
     score that cancels to exactly 0.0 in the oracle can be 5e-16 here - constant or silent audio does that; the
     documented spectrogram tolerance, not a selection error); anything else is a failure."""
     a = batch.arrays
@@ -118,12 +138,28 @@ def compare(batch, ref_lists):
         if got == want:
             continue
         c = next(c for c in range(len(ref)) if got[c] != want[c])
-        own = {w[:2]: (w, sc) for w, sc in zip(want, ws)}
-        same_records = sorted(got) == sorted(want) and all(abs(own[g[:2]][1] - sc) < 1e-9 for g, sc in zip(got, gs))
-        if not same_records:
+        # match candidates by position: the same set of (abs_time, abs_freq)?
+        gpos, wpos = {g[:2]: (g, sc) for g, sc in zip(got, gs)}, {w[:2]: (w, sc) for w, sc in zip(want, ws)}
+        if len(gpos) != len(got) or set(gpos) != set(wpos):
             return "slot %d cand %d: %r vs %r" % (i, c, got[c], want[c])
-        near = "near-tie: slot %d from cand %d on, same records, order differs among scores equal to 1e-9 (%r vs %r)" % (
-            i, c, got[c][:2], want[c][:2])
+        notes = []
+        # (a) decode records that differ at the same position.  BP on a word that does not converge is chaotic: the
+        # ~1e-11 dB by which two FFT factorisations differ can change ldpc_errors of a failing word.  Decided by running the
+        # GPU's LLR + BP on the ORACLE's spectrogram for the differing candidates: equal records there mean the
+        # difference is the spectrogram tolerance, not the decode kernels.
+        bad = [p_ for p_ in wpos if gpos[p_][0] != wpos[p_][0]]
+        if bad:
+            if ctx is None or not all(rerun_on_oracle_spectrogram(ctx, i, wpos[p_][0]) for p_ in bad[:8]):
+                return "slot %d position %r: %r vs %r" % (i, bad[0], gpos[bad[0]][0], wpos[bad[0]][0])
+            notes.append("spectrogram-rounding: slot %d, %d candidate record(s) (first: %r %r vs %r) equal once LLR + BP run on "
+                         "the oracle's spectrogram" % (i, len(bad), bad[0], gpos[bad[0]][0][2:4], wpos[bad[0]][0][2:4]))
+        # (b) order: may differ only among scores equal to 1e-9
+        if [g[:2] for g in got] != [w[:2] for w in want]:
+            if not all(abs(gpos[p_][1] - wpos[p_][1]) < 1e-9 for p_ in wpos):
+                return "slot %d cand %d: %r vs %r" % (i, c, got[c], want[c])
+            notes.append("near-tie: slot %d from cand %d on, order differs among scores equal to 1e-9 (%r vs %r)" % (
+                i, c, got[c][:2], want[c][:2]))
+        near = "; ".join(notes)
     return near
 
 
@@ -156,10 +192,10 @@ def run(trials, seed):
             if len(batch.to_lists()) and any(batch.to_lists()):
                 failures.append(dict(desc, why="reference: input shorter than a window; GPU returned decodes"))
             continue
-        why = compare(batch, ref)
+        why = compare(batch, ref, (fs, b, s, waves, kw, masks))
         records += sum(len(r) for r in ref if r is not None)
         decoded += sum(1 for r in ref if r is not None for c in r if c["ok"])
-        if why and why.startswith("near-tie"):
+        if why and why.startswith(("near-tie", "spectrogram-rounding")):
             near_ties.append(dict(desc, why=why))
         elif why:
             failures.append(dict(desc, why=why))
