@@ -302,15 +302,17 @@ def main():
     torch.cuda.synchronize()
 
     # ---- timed region: K steps, device-resident input ----
-    sampler.recording = True
     L.ft8b_stage_timing(1)
     launches0 = L.ft8b_launch_count()
-    barrier()
+    barrier()                          # (the first NCCL barrier of a multi-rank run takes seconds: not part of the clock samples)
+    sampler.recording = True
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
         dec.run(waves)
     e1.record()
+    torch.cuda.synchronize()
+    sampler.recording = False
     barrier()
     ms_total = e0.elapsed_time(e1)
     launches = L.ft8b_launch_count() - launches0
@@ -318,7 +320,6 @@ def main():
     stage_n = (C.c_int64 * 5)()
     L.ft8b_stage_times(stage_ms, stage_n)
     L.ft8b_stage_timing(0)
-    sampler.recording = False
     n_in_region = len(sampler.samples)
     if rank == 0 and n_in_region < 3:
         # the region is short (K x 16 ms): when NVML answered fewer than three times inside it, keep the SAME load running
