@@ -11,7 +11,10 @@
  *   - return 0 = OK, negative = argument / capability error (FT8B_ERR_*), positive = cudaError_t;
  *     ft8b_last_error() returns a thread-local description of the last failure.
  *   - entry points that take a `stream`: every data pointer is a DEVICE pointer owned by the
- *     caller (contiguous, 16-byte aligned); the library allocates nothing per call.
+ *     caller (contiguous, 16-byte aligned); the library allocates nothing per call - except a
+ *     stream-ordered scratch (cudaMallocAsync / cudaFreeAsync on `stream`) on two rare paths: frames
+ *     of more than 14 336 transform points (sample rates from 96 kHz up) and candidate lists above
+ *     4096 entries.
  *     Per-(device, nfft) window/twiddle tables are created on first use (mutex-guarded,
  *     synchronous) and live until ft8b_release().  `stream` is a cudaStream_t passed as void*
  *     (NULL = legacy default stream); every call is asynchronous on it.
@@ -23,7 +26,8 @@
  *   - there is NO CPU fallback: without a CUDA device every compute call fails.
  *
  * Layouts (row-major, last index fastest)
- *   wave    [n_slots][slot_stride]            float32 / float64 / int16 samples, n_samples used per slot
+ *   wave    [n_slots][slot_stride]            float32 / float64 / int16 samples (or complex64 / complex128
+ *                                             baseband), n_samples used per slot
  *   mag     [n_slots][T][F]                   dB spectrogram, time-major (the reference's
  *                                             FT8Waterfall.mag is [F][T]; the Python mirror transposes)
  *   scores  [n_slots][nt][nf]                 Costas sync scores in the reference's scan order
